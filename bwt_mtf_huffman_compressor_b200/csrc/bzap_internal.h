@@ -1,0 +1,120 @@
+// bzap_internal.h -- context, scratch arena and the device-level stage entry points shared by
+// the translation units of libbzap.so.  Not part of the public ABI (include/bzap.h is).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <stdio.h>
+#include "../../include/bzap.h"
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+struct bzap_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;      // stream all work is issued on
+    cudaStream_t own_stream = nullptr;
+    // scratch arena in HBM: one allocation, bump-allocated per top-level call
+    u8 *arena = nullptr;
+    size_t arena_cap = 0;
+    size_t arena_off = 0;
+    // small pinned host mailbox for flags / histograms coming back from the device
+    u8 *mailbox = nullptr;               // 64 KiB pinned
+    cudaEvent_t ev[8] = {};
+    bzap_stats stats = {};
+    u64 launches = 0;
+    char err[256] = {0};
+};
+
+#define BZAP_MAILBOX_BYTES (64 * 1024)
+
+// ---- error plumbing ------------------------------------------------------------------------
+int bzap_fail(bzap_ctx *ctx, int code, const char *fmt, ...);
+#define CU(ctx, call)                                                                             \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return bzap_fail(ctx, BZAP_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,       \
+                             cudaGetErrorString(e_));                                             \
+    } while (0)
+#define RET(call)                                                                                 \
+    do {                                                                                          \
+        int r_ = (call);                                                                          \
+        if (r_ != BZAP_OK) return r_;                                                             \
+    } while (0)
+// every kernel launch goes through this so that stats.kernel_launches is a true count
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                                               \
+    do {                                                                                          \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                          \
+        ++(ctx)->launches;                                                                        \
+    } while (0)
+
+// ---- arena ------------------------------------------------------------------------------------
+int arena_reserve(bzap_ctx *ctx, size_t bytes);     // grow (sync + realloc) if needed, reset offset
+void *arena_alloc(bzap_ctx *ctx, size_t bytes);     // 256-byte aligned bump allocation, nullptr if full
+template <typename T> static inline T *arena_get(bzap_ctx *ctx, size_t count)
+{
+    return (T *)arena_alloc(ctx, count * sizeof(T));
+}
+size_t scratch_bytes_compress(size_t n);
+size_t scratch_bytes_decompress(size_t n, size_t payload);
+
+// ---- host-side Huffman model (huffman_host.cpp) -------------------------------------------
+struct CodeTable {
+    u64 code[256];
+    u8 len[256];
+    int max_len;
+};
+// decode tables: primary LUT of 1<<DEC_PRIMARY_BITS u16 entries, then 256-entry sub tables
+#define DEC_PRIMARY_BITS 12
+#define DEC_SUB_BITS 8
+struct DecodeTables {
+    u16 *entries;      // malloc'ed, n_entries u16
+    size_t n_entries;
+    int max_len;       // depth of the tree
+    int single_leaf;   // tree is one leaf: empty code (main.cpp:137-140)
+    u8 single_value;
+};
+int huff_build_tree(const u64 freq[256], const u8 *order, int n_leaves, bzap_tree *t);
+int huff_code_table(const bzap_tree *t, CodeTable *ct);      // BZAP_ERR_TOO_LARGE if a code > 64 bits
+int huff_tree_to_bytes(const bzap_tree *t, u8 *out, size_t *len);
+int huff_bytes_to_tree(const u8 *bytes, size_t len, bzap_tree *t);
+int huff_decode_tables(const bzap_tree *t, DecodeTables *dt);
+void huff_free_decode_tables(DecodeTables *dt);
+u64 huff_total_bits(const u64 freq[256], const CodeTable *ct);
+
+// ---- device-level stages (all pointers are device pointers, work on ctx->stream) ------------
+// forward BWT (bwt.cu): writes last column, returns primary index on the host (syncs)
+int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n, u8 *d_last, u64 *primary);
+// forward / inverse MTF (mtf.cu)
+int dev_mtf(bzap_ctx *ctx, const u8 *d_in, size_t n, u8 *d_out);
+int dev_imtf(bzap_ctx *ctx, const u8 *d_in, size_t n, u8 *d_out);
+// histogram + first appearance order (huffman_enc.cu), syncs
+int dev_hist(bzap_ctx *ctx, const u8 *d_in, size_t n, u64 freq[256], u8 order[256], int *n_leaves);
+// bit packer (huffman_enc.cu): ORs the code stream into d_file starting at bit `bit_base`
+// (d_file zeroed by the caller, 16-byte aligned, with >= 32 bytes of slack after the last bit)
+int dev_huff_encode(bzap_ctx *ctx, const u8 *d_in, size_t n, const CodeTable *ct, u8 *d_file, u64 bit_base);
+// decoder (huffman_dec.cu): d_payload must be 4-byte aligned with >= 64 zero bytes of slack
+int dev_huff_decode(bzap_ctx *ctx, const u8 *d_payload, size_t payload_len, const DecodeTables *dt, size_t n,
+                    u8 *d_out);
+// inverse BWT (ibwt.cu)
+int dev_ibwt(bzap_ctx *ctx, const u8 *d_last, size_t n, u64 primary, u8 *d_out);
+
+// ---- radix sort building blocks (radix_sort.cu) ----------------------------------------------
+// LSD onesweep over `nbits` low bits of 64-bit keys with 32-bit payloads.  d_hist holds
+// ceil(nbits/8) x 256 digit counts already accumulated by the caller's key-producing kernel.
+// vals_in == nullptr means "payload = element index" (materialised by the first executed pass).
+// On return *out_keys / *out_vals point at the buffers holding the result (vals may be nullptr
+// when no pass executed and the payload is still the identity).
+struct SortBuffers {
+    u64 *keys[2];
+    u32 *vals[2];
+};
+int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, int nbits, u32 *d_hist, bool vals_are_iota,
+                     u64 **out_keys, u32 **out_vals, int *passes_run);
+// stable counting sort of positions by byte value: T[r] = position of the r-th smallest (byte, pos)
+// (main.cpp:67); d_cum receives the 257 exclusive byte counts
+int dev_sort_positions_by_byte(bzap_ctx *ctx, const u8 *d_bytes, u32 n, u32 *d_T, u32 *d_cum);
+size_t sort_scratch_bytes(u32 n);

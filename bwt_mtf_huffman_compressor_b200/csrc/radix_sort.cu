@@ -1,0 +1,286 @@
+// radix_sort.cu -- hand-written onesweep LSD radix sort (8-bit digits) for sm_100a.
+//
+// Replaces std::stable_sort in bwt() (main.cpp:82) and bwt_reverse() (main.cpp:67).  One pass =
+// ONE kernel that reads every (key, payload) once and writes it once:
+//   * digit counts for all passes are accumulated up front by the kernel that PRODUCES the keys
+//     (fused, bwt.cu) or by radix_hist_u8 below, then turned into global digit offsets;
+//   * each 256-thread block takes a tile by atomic ticket, ranks its keys with warp-level
+//     match-any multisplit into per-warp shared-memory digit counters, publishes the tile's 256
+//     digit counts and resolves its global base per digit by decoupled look-back over the
+//     previous tiles' status words (flag+count in one 32-bit word);
+//   * keys and payloads are regrouped by digit in shared memory and written out as contiguous
+//     per-digit runs.
+// Passes whose digit is constant over all keys are skipped on the host after reading back the
+// per-pass "trivial" flags; that is what makes periodic inputs (all keys equal) cheap.
+#include "device_common.cuh"
+
+#define RS_BLOCK 256
+#define RS_WARPS (RS_BLOCK / 32)
+#define RS_FLAG_AGG (1u << 30)
+#define RS_FLAG_INCL (2u << 30)
+#define RS_VALUE_MASK ((1u << 30) - 1)
+
+template <typename KeyT, int ITEMS> struct RsSmem {
+    KeyT keys[RS_BLOCK * ITEMS];
+    u32 vals[RS_BLOCK * ITEMS];
+    u32 whist[RS_WARPS][256];
+    u32 adj[256];
+    u32 scan_tmp[40];
+    u32 ticket;
+};
+
+template <typename KeyT> __device__ __forceinline__ u32 digit_of(KeyT k, int shift)
+{
+    return (u32)(k >> shift) & 0xffu;
+}
+
+// offsets = exclusive global digit offsets of this pass (256); status = tiles*256 zeroed words
+template <typename KeyT, int ITEMS, bool IOTA_VALS, bool WRITE_KEYS>
+__global__ void __launch_bounds__(RS_BLOCK)
+onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out, const u32 *__restrict__ vals_in,
+                     u32 *__restrict__ vals_out, u32 n, int shift, const u32 *__restrict__ offsets, u32 *status,
+                     u32 *ticket)
+{
+    extern __shared__ __align__(16) u8 smem_raw[];
+    RsSmem<KeyT, ITEMS> &S = *reinterpret_cast<RsSmem<KeyT, ITEMS> *>(smem_raw);
+    constexpr u32 TILE = RS_BLOCK * ITEMS;
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const u32 tile = take_ticket(ticket, &S.ticket);
+    const u32 tile_base = tile * TILE;
+    const u32 valid = min(TILE, n - tile_base);
+    const u32 wbase = tile_base + warp * (32u * ITEMS);
+
+    KeyT key[ITEMS];
+    u32 val[ITEMS];
+    u32 rnk[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        u32 idx = wbase + j * 32u + lane;
+        key[j] = idx < n ? keys_in[idx] : (KeyT)~(KeyT)0;
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        u32 idx = wbase + j * 32u + lane;
+        if (IOTA_VALS) val[j] = idx;
+        else val[j] = idx < n ? vals_in[idx] : 0u;
+    }
+    for (u32 i = lane; i < 256; i += 32) S.whist[warp][i] = 0;
+    __syncwarp();
+
+    // warp-level multisplit: rank of each key among the warp's keys with the same digit
+    u32 *wh = S.whist[warp];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        u32 d = digit_of(key[j], shift);
+        u32 m = __match_any_sync(FULL_MASK, d);
+        u32 leader = (u32)__ffs(m) - 1u;
+        u32 prev = 0;
+        if (lane == leader) {
+            prev = wh[d];
+            wh[d] = prev + (u32)__popc(m);
+        }
+        prev = __shfl_sync(FULL_MASK, prev, leader);
+        rnk[j] = prev + (u32)__popc(m & lanemask_lt());
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // thread b owns digit b: prefix over warps, publish, scan over digits, look back
+    {
+        const u32 b = tid;
+        u32 run = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            u32 t = S.whist[w][b];
+            S.whist[w][b] = run;
+            run += t;
+        }
+        const u32 count = run;
+        u32 *my_status = status + (size_t)tile * 256 + b;
+        if (tile == 0) st_relaxed(my_status, RS_FLAG_INCL | count);
+        else st_relaxed(my_status, RS_FLAG_AGG | count);
+        u32 total;
+        u32 tile_start = block_exclusive_sum(count, S.scan_tmp, &total);
+        u32 excl = 0;
+        if (tile > 0) {
+            int t = (int)tile - 1;
+            while (true) {
+                const u32 *p = status + (size_t)t * 256 + b;
+                u32 s;
+                do { s = ld_relaxed(p); } while ((s >> 30) == 0);
+                excl += s & RS_VALUE_MASK;
+                if ((s >> 30) == 2) break;
+                --t;
+            }
+            st_relaxed(my_status, RS_FLAG_INCL | (excl + count));
+        }
+        S.adj[b] = offsets[b] + excl - tile_start;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) S.whist[w][b] += tile_start;
+    }
+    __syncthreads();
+
+    // regroup by digit in shared memory
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        u32 d = digit_of(key[j], shift);
+        u32 pos = wh[d] + rnk[j];
+        S.keys[pos] = key[j];
+        S.vals[pos] = val[j];
+    }
+    __syncthreads();
+
+    // contiguous per-digit runs go out; padding keys (digit 255, highest tile index) sit last
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        u32 idx = tid + i * RS_BLOCK;
+        if (idx < valid) {
+            KeyT k = S.keys[idx];
+            u32 g = S.adj[digit_of(k, shift)] + idx;
+            if (WRITE_KEYS) keys_out[g] = k;
+            vals_out[g] = S.vals[idx];
+        }
+    }
+}
+
+// ---- digit offsets -------------------------------------------------------------------------------
+// hist: passes x 256 counts.  offsets: passes x 256 exclusive sums.  trivial[p] = 1 when one digit
+// value holds all n keys (the pass is the identity permutation).
+__global__ void radix_offsets_kernel(const u32 *__restrict__ hist, u32 *__restrict__ offsets, u32 *trivial, u32 n,
+                                     int passes)
+{
+    __shared__ u32 s_tmp[40];
+    for (int p = 0; p < passes; ++p) {
+        u32 c = hist[p * 256 + threadIdx.x];
+        u32 total;
+        u32 ex = block_exclusive_sum(c, s_tmp, &total);
+        offsets[p * 256 + threadIdx.x] = ex;
+        if (c == n) trivial[p] = 1;
+    }
+}
+
+// byte histogram for the inverse-BWT counting sort (u8 keys, one digit)
+__global__ void __launch_bounds__(256) radix_hist_u8_kernel(const u8 *__restrict__ in, u32 n, u32 *hist)
+{
+    __shared__ u32 s_h[256];
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 nvec = n / 16;
+    const uint4 *in4 = reinterpret_cast<const uint4 *>(in);
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
+        uint4 v = in4[i];
+        u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            atomicAdd(&s_h[w[k] & 0xff], 1u);
+            atomicAdd(&s_h[(w[k] >> 8) & 0xff], 1u);
+            atomicAdd(&s_h[(w[k] >> 16) & 0xff], 1u);
+            atomicAdd(&s_h[w[k] >> 24], 1u);
+        }
+    }
+    for (u32 i = nvec * 16 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        atomicAdd(&s_h[in[i]], 1u);
+    __syncthreads();
+    u32 c = s_h[threadIdx.x];
+    if (c) atomicAdd(&hist[threadIdx.x], c);
+}
+
+// cum[0..256]: exclusive byte counts (cum[256] = n)
+__global__ void radix_cum_u8_kernel(const u32 *__restrict__ hist, u32 *__restrict__ cum)
+{
+    __shared__ u32 s_tmp[40];
+    u32 c = hist[threadIdx.x];
+    u32 total;
+    u32 ex = block_exclusive_sum(c, s_tmp, &total);
+    cum[threadIdx.x] = ex;
+    if (threadIdx.x == 255) cum[256] = ex + c;
+}
+
+// ---- host drivers ------------------------------------------------------------------------------
+#define RS_ITEMS_64 16
+#define RS_ITEMS_8 16
+
+size_t sort_scratch_bytes(u32 n)
+{
+    size_t tiles = ((size_t)n + RS_BLOCK * RS_ITEMS_64 - 1) / (RS_BLOCK * RS_ITEMS_64);
+    // 8 passes of status words + tickets + offsets + flags
+    return 8 * (tiles * 256 * sizeof(u32) + 256) + 64 * 1024;
+}
+
+template <typename K> static int set_smem_attr(bzap_ctx *ctx, K kernel, size_t bytes)
+{
+    CU(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return BZAP_OK;
+}
+
+int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, int nbits, u32 *d_hist, bool vals_are_iota, u64 **out_keys,
+                     u32 **out_vals, int *passes_run)
+{
+    constexpr int ITEMS = RS_ITEMS_64;
+    const int passes = (nbits + 7) / 8;
+    const u32 tiles = (n + RS_BLOCK * ITEMS - 1) / (RS_BLOCK * ITEMS);
+    const size_t status_words = (size_t)tiles * 256;
+    // control block: offsets[8][256], trivial[8], tickets[8], then status per pass
+    u32 *d_ctl = arena_get<u32>(ctx, 8 * 256 + 16 + passes * status_words);
+    if (!d_ctl) return bzap_fail(ctx, BZAP_ERR_NOMEM, "sort scratch");
+    u32 *d_offsets = d_ctl, *d_trivial = d_ctl + 8 * 256, *d_ticket = d_trivial + 8, *d_status = d_ticket + 8;
+    CU(ctx, cudaMemsetAsync(d_trivial, 0, (16 + passes * status_words) * sizeof(u32), ctx->stream));
+    LAUNCH(ctx, radix_offsets_kernel, 1, 256, 0, d_hist, d_offsets, d_trivial, n, passes);
+    u32 *h_trivial = (u32 *)ctx->mailbox;
+    CU(ctx, cudaMemcpyAsync(h_trivial, d_trivial, 8 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+
+    auto k_iota = onesweep_pass_kernel<u64, ITEMS, true, true>;
+    auto k_vals = onesweep_pass_kernel<u64, ITEMS, false, true>;
+    const size_t smem = sizeof(RsSmem<u64, ITEMS>);
+    static bool attr_done = false;
+    if (!attr_done) {
+        RET(set_smem_attr(ctx, k_iota, smem));
+        RET(set_smem_attr(ctx, k_vals, smem));
+        attr_done = true;
+    }
+    int cur = 0, run = 0;
+    bool have_vals = !vals_are_iota;
+    for (int p = 0; p < passes; ++p) {
+        if (h_trivial[p]) continue;
+        if (!have_vals)
+            LAUNCH(ctx, k_iota, tiles, RS_BLOCK, smem, b->keys[cur], b->keys[cur ^ 1], (const u32 *)nullptr,
+                   b->vals[cur ^ 1], n, 8 * p, d_offsets + p * 256, d_status + (size_t)p * status_words, d_ticket + p);
+        else
+            LAUNCH(ctx, k_vals, tiles, RS_BLOCK, smem, b->keys[cur], b->keys[cur ^ 1], b->vals[cur], b->vals[cur ^ 1], n,
+                   8 * p, d_offsets + p * 256, d_status + (size_t)p * status_words, d_ticket + p);
+        have_vals = true;
+        cur ^= 1;
+        ++run;
+    }
+    CU(ctx, cudaGetLastError());
+    *out_keys = b->keys[cur];
+    *out_vals = have_vals ? b->vals[cur] : nullptr;
+    if (passes_run) *passes_run = run;
+    return BZAP_OK;
+}
+
+int dev_sort_positions_by_byte(bzap_ctx *ctx, const u8 *d_bytes, u32 n, u32 *d_T, u32 *d_cum)
+{
+    constexpr int ITEMS = RS_ITEMS_8;
+    const u32 tiles = (n + RS_BLOCK * ITEMS - 1) / (RS_BLOCK * ITEMS);
+    const size_t status_words = (size_t)tiles * 256;
+    u32 *d_ctl = arena_get<u32>(ctx, 256 + 8 + status_words);
+    if (!d_ctl) return bzap_fail(ctx, BZAP_ERR_NOMEM, "sort scratch");
+    u32 *d_hist = d_ctl, *d_ticket = d_ctl + 256, *d_status = d_ctl + 264;
+    CU(ctx, cudaMemsetAsync(d_ctl, 0, (264 + status_words) * sizeof(u32), ctx->stream));
+    u32 grid = min((n / 16 + 255) / 256 + 1, 148u * 8u);
+    LAUNCH(ctx, radix_hist_u8_kernel, grid, 256, 0, d_bytes, n, d_hist);
+    LAUNCH(ctx, radix_cum_u8_kernel, 1, 256, 0, d_hist, d_cum);
+    auto k = onesweep_pass_kernel<u8, ITEMS, true, false>;
+    const size_t smem = sizeof(RsSmem<u8, ITEMS>);
+    static bool attr_done = false;
+    if (!attr_done) {
+        RET(set_smem_attr(ctx, k, smem));
+        attr_done = true;
+    }
+    LAUNCH(ctx, k, tiles, RS_BLOCK, smem, d_bytes, (u8 *)nullptr, (const u32 *)nullptr, d_T, n, 0, d_cum, d_status,
+           d_ticket);
+    CU(ctx, cudaGetLastError());
+    return BZAP_OK;
+}
