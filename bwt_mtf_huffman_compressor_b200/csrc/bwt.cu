@@ -187,7 +187,6 @@ __global__ void __launch_bounds__(256) bwt_gather_kernel(const u8 *__restrict__ 
     }
 }
 
-__global__ void radix_hist_u8_kernel(const u8 *__restrict__ in, u32 n, u32 *hist);   // radix_sort.cu
 
 // ---- host driver -----------------------------------------------------------------------------------------
 static inline u32 grid_for(size_t work_items, u32 per_block, u32 cap = 148u * 16u)
@@ -221,7 +220,7 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
 
     // round 0: byte histogram stands in for all eight digit histograms of the 8-byte windows
     CU(ctx, cudaMemsetAsync(d_hist4, 0, 256 * sizeof(u32), ctx->stream));
-    LAUNCH(ctx, radix_hist_u8_kernel, grid_for(n / 16 + 1, 256, 148 * 8), 256, 0, d_in, n, d_hist4);
+    RET(dev_byte_hist(ctx, d_in, n, d_hist4));
     LAUNCH(ctx, bwt_spread_hist_kernel, 1, 256, 0, d_hist4, 1, d_hist8);
     LAUNCH(ctx, bwt_init_keys_kernel, grid_for((n + IK_TILE - 1) / IK_TILE, 1, 148 * 8), IK_BLOCK, 0, d_in, n, sb.keys[0]);
 

@@ -118,3 +118,5 @@ int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, int nbits, u32 *d_his
 // (main.cpp:67); d_cum receives the 257 exclusive byte counts
 int dev_sort_positions_by_byte(bzap_ctx *ctx, const u8 *d_bytes, u32 n, u32 *d_T, u32 *d_cum);
 size_t sort_scratch_bytes(u32 n);
+// 256-bin byte histogram accumulated into d_hist256 (caller zeroes it)
+int dev_byte_hist(bzap_ctx *ctx, const u8 *d_bytes, u32 n, u32 *d_hist256);

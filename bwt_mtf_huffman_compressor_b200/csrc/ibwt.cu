@@ -1,0 +1,163 @@
+// ibwt.cu -- inverse Burrows-Wheeler transform: counting-sort map + parallel list ranking.
+//
+// Replaces bwt_reverse (main.cpp:61-75):
+//     l_shift = stable_sort(iota(N)) by L[.]            (main.cpp:65-67)
+//     repeat N times: out[i] = L[l_shift[row]]; row = l_shift[row]     (main.cpp:70-73)
+// With T = l_shift (built by one onesweep counting-sort pass on the byte keys, radix_sort.cu) and
+// F(r) = L[T[r]] = the byte whose cumulative-count interval contains r, the walk is
+//     x_0 = primary,  x_{i+1} = T[x_i],  out[i] = F(x_i).
+// T is a permutation and may have MANY cycles (periodic input: "abab" -> T = [2,3,0,1]); the walk
+// stays on the cycle of `primary` and laps it N / cycle_length times.  It is parallelised by
+// work-efficient list ranking with pseudo-random splitters:
+//   1. one splitter row per bucket of IB_STRIDE rows (hashed offset), plus `primary` itself;
+//   2. ibwt_walk_len_kernel : every splitter walks T until it lands on the next splitter ->
+//      reduced list (next splitter, sublist length);
+//   3. ibwt_wyllie_kernel   : pointer jumping on the reduced list, cut open at `primary`, gives
+//      every splitter on primary's cycle its distance to the end, hence its output offset;
+//   4. ibwt_walk_write_kernel: every reachable splitter walks again and writes its bytes;
+//   5. ibwt_extend_kernel   : out[i] = out[i mod cycle_length] when the cycle is shorter than N.
+// Nothing assumes a single list, so splitters on other cycles are simply never reached.
+#include "device_common.cuh"
+
+#define IB_STRIDE_LOG 6
+#define IB_STRIDE (1u << IB_STRIDE_LOG)
+#define IB_NIL 0xffffffffu
+
+__device__ __forceinline__ u32 ib_hash(u32 x)
+{
+    x ^= x >> 16; x *= 0x7feb352du;
+    x ^= x >> 15; x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
+}
+// row of the splitter of bucket b
+__device__ __forceinline__ u32 ib_splitter_row(u32 b, u32 n)
+{
+    u32 lo = b << IB_STRIDE_LOG;
+    u32 span = min(IB_STRIDE, n - lo);
+    u32 h = ib_hash(b);
+    return lo + (span == IB_STRIDE ? (h & (IB_STRIDE - 1u)) : h % span);
+}
+// node id of the splitter sitting on `row`, or IB_NIL.  Node `nb` (= number of buckets) is `primary`.
+__device__ __forceinline__ u32 ib_node_of(u32 row, u32 n, u32 nb, u32 primary)
+{
+    if (row == primary) return nb;
+    u32 b = row >> IB_STRIDE_LOG;
+    return ib_splitter_row(b, n) == row ? b : IB_NIL;
+}
+
+// node[j] = (next << 32) | len ; a regular splitter that coincides with `primary` is dropped
+// (next = NIL, len = 0): node nb covers that row.
+__global__ void __launch_bounds__(256)
+ibwt_walk_len_kernel(const u32 *__restrict__ T, u32 n, u32 nb, u32 primary, u64 *__restrict__ node)
+{
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > nb) return;
+    u32 row = j == nb ? primary : ib_splitter_row(j, n);
+    if (j < nb && row == primary) { node[j] = ((u64)IB_NIL << 32); return; }
+    u32 len = 0, nx;
+    do {
+        row = T[row];
+        ++len;
+        nx = ib_node_of(row, n, nb, primary);
+    } while (nx == IB_NIL);
+    // the list is cut open in front of `primary`: the node that reaches it becomes the tail
+    node[j] = ((u64)(nx == nb ? IB_NIL : nx) << 32) | len;
+}
+
+// one pointer-jumping round: dist[j] += dist[next[j]]; next[j] = next[next[j]]
+__global__ void __launch_bounds__(256) ibwt_wyllie_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, u32 count)
+{
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    u64 a = in[j];
+    u32 nx = (u32)(a >> 32);
+    if (nx != IB_NIL) {
+        u64 b = in[nx];
+        a = (b & 0xffffffff00000000ull) | (u32)((u32)a + (u32)b);
+    }
+    out[j] = a;
+}
+
+// F(r): byte c with cum[c] <= r < cum[c+1]
+__device__ __forceinline__ u32 ib_first_col(const u32 *s_cum, u32 r)
+{
+    u32 lo = 0, hi = 256;                 // invariant: cum[lo] <= r < cum[hi]
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        u32 mid = (lo + hi) >> 1;
+        if (s_cum[mid] <= r) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// dist[j] (from the ranking) = bytes from splitter j to the end of the opened list; the list holds
+// cycle_len = dist[nb] bytes, so splitter j starts writing at cycle_len - dist[j].
+__global__ void __launch_bounds__(256)
+ibwt_walk_write_kernel(const u32 *__restrict__ T, u32 n, u32 nb, u32 primary, const u64 *__restrict__ len_node,
+                       const u64 *__restrict__ ranked, const u32 *__restrict__ cum, u8 *__restrict__ out)
+{
+    __shared__ u32 s_cum[257];
+    for (u32 i = threadIdx.x; i < 257; i += blockDim.x) s_cum[i] = cum[i];
+    __syncthreads();
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > nb) return;
+    const u64 rk = ranked[j];
+    if ((u32)(rk >> 32) != IB_NIL) return;              // never reaches `primary`: another cycle
+    const u32 len = (u32)len_node[j];
+    if (len == 0) return;                               // dropped duplicate of `primary`
+    const u32 cycle_len = (u32)ranked[nb];
+    u32 o = cycle_len - (u32)rk;
+    u32 row = j == nb ? primary : ib_splitter_row(j, n);
+    for (u32 t = 0; t < len; ++t) {
+        out[o + t] = (u8)ib_first_col(s_cum, row);      // out[i] = L[T[x_i]] = F(x_i)   (main.cpp:71)
+        row = T[row];
+    }
+}
+
+__global__ void __launch_bounds__(256) ibwt_extend_kernel(u8 *out, u32 n, u32 cycle_len)
+{
+    for (u32 i = cycle_len + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        out[i] = out[i % cycle_len];
+}
+
+int dev_ibwt(bzap_ctx *ctx, const u8 *d_last, size_t n64, u64 primary64, u8 *d_out)
+{
+    if (n64 == 0) return BZAP_OK;
+    if (n64 > BZAP_MAX_BLOCK) return bzap_fail(ctx, BZAP_ERR_TOO_LARGE, "block of %zu bytes", n64);
+    if (primary64 >= n64) return bzap_fail(ctx, BZAP_ERR_CORRUPT, "primary index %llu >= N %zu",
+                                           (unsigned long long)primary64, n64);
+    const u32 n = (u32)n64, primary = (u32)primary64;
+    const u32 nb = (n + IB_STRIDE - 1) >> IB_STRIDE_LOG;
+    const u32 nodes = nb + 1;
+    u32 *d_T = arena_get<u32>(ctx, n);
+    u32 *d_cum = arena_get<u32>(ctx, 260);
+    u64 *d_len = arena_get<u64>(ctx, nodes);
+    u64 *d_rank[2] = {arena_get<u64>(ctx, nodes), arena_get<u64>(ctx, nodes)};
+    if (!d_T || !d_cum || !d_len || !d_rank[0] || !d_rank[1]) return bzap_fail(ctx, BZAP_ERR_NOMEM, "ibwt scratch");
+    RET(dev_sort_positions_by_byte(ctx, d_last, n, d_T, d_cum));
+    const u32 nblk = (nodes + 255) / 256;
+    LAUNCH(ctx, ibwt_walk_len_kernel, nblk, 256, 0, d_T, n, nb, primary, d_len);
+    // pointer jumping: after r rounds every node has jumped 2^r links
+    int cur = 0;
+    const u64 *src = d_len;
+    for (u64 span = 1; span < nodes; span <<= 1) {
+        LAUNCH(ctx, ibwt_wyllie_kernel, nblk, 256, 0, src, d_rank[cur], nodes);
+        src = d_rank[cur];
+        cur ^= 1;
+    }
+    if (src == d_len) {                                  // single node: ranking is the identity
+        CU(ctx, cudaMemcpyAsync(d_rank[0], d_len, nodes * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
+        src = d_rank[0];
+    }
+    LAUNCH(ctx, ibwt_walk_write_kernel, nblk, 256, 0, d_T, n, nb, primary, d_len, src, d_cum, d_out);
+    u64 *h_cycle = (u64 *)(ctx->mailbox + 1056);
+    CU(ctx, cudaMemcpyAsync(h_cycle, src + nb, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    const u32 cycle_len = (u32)*h_cycle;
+    if ((u32)(*h_cycle >> 32) != IB_NIL || cycle_len == 0 || cycle_len > n)
+        return bzap_fail(ctx, BZAP_ERR_CUDA, "list ranking failed (cycle %u)", cycle_len);
+    if (cycle_len < n) LAUNCH(ctx, ibwt_extend_kernel, 148 * 8, 256, 0, d_out, n, cycle_len);
+    CU(ctx, cudaGetLastError());
+    return BZAP_OK;
+}

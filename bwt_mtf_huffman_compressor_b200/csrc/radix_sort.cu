@@ -260,6 +260,13 @@ int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, int nbits, u32 *d_his
     return BZAP_OK;
 }
 
+int dev_byte_hist(bzap_ctx *ctx, const u8 *d_bytes, u32 n, u32 *d_hist256)
+{
+    u32 grid = min((n / 16 + 255) / 256 + 1, 148u * 8u);
+    LAUNCH(ctx, radix_hist_u8_kernel, grid, 256, 0, d_bytes, n, d_hist256);
+    return BZAP_OK;
+}
+
 int dev_sort_positions_by_byte(bzap_ctx *ctx, const u8 *d_bytes, u32 n, u32 *d_T, u32 *d_cum)
 {
     constexpr int ITEMS = RS_ITEMS_8;

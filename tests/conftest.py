@@ -1,0 +1,31 @@
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on a B200 with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def calgary():
+    from bwt_mtf_huffman_compressor_b200 import workloads
+    return workloads.calgary()
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _build_oracle():
+    import oracle_lib
+    oracle_lib.orc()   # builds oracle/liboracle.so if missing (gcc only)
