@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on its named config.
+
+  python bench.py --gpus N --steps K --warmup W            (ours; torchrun-launched for N > 1)
+  python bench.py --impl reference --gpus N --steps K --warmup W   (the reference's CPU path)
+
+Workload (config.workload "text64m"): BASELINE config 3, one 64 MiB English-like text block
+(SURVEY 8d C3 generator, seed 0x5EED0064 + rank) compressed as ONE whole-file BWT block and
+decompressed again.  A step = compress + decompress of that block; the metric is uncompressed
+input MB/s over the round trip (10^6 bytes / s), counted only when the compressed file equals the
+reference's golden bytes and the round trip is bit exact (checked during warm-up, every rank).
+  value : inputs resident in HBM (bzap_compress_device / bzap_decompress_device), CUDA events
+  e2e   : same through the host-buffer C ABI (bzap_compress / bzap_decompress) from pinned host
+          memory, H2D and D2H copies inside the timed region
+N > 1: independent files, one per rank per step, no collective on the data path (weak scaling).
+Other workloads (--workload calgary | degenerate) are reported as extra lines on stderr only.
+"""
+import argparse
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "compress+decompress round-trip throughput of uncompressed bytes (bit-exact, byte-identical file)"
+UNIT = "MB/s"
+N_TEXT = 1 << 26
+BASE_SEED = 0x5EED0064
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 8 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 8:
+                for k, nm in enumerate(names):
+                    if r[4 + k].lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import bwt_mtf_huffman_compressor_b200 as bz
+    from bwt_mtf_huffman_compressor_b200 import workloads as W
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.size
+    data = W.synthetic_text(n, BASE_SEED + rank)
+    ctx = bz.Context(local)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    cap = bz.compress_bound(n)
+    h_in = torch.from_numpy(data.copy()).pin_memory()
+    h_file = torch.empty(cap, dtype=torch.uint8).pin_memory()
+    h_back = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d_in = h_in.cuda()
+    d_file = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    d_back = torch.empty(n, dtype=torch.uint8, device="cuda")
+
+    # ---- validity gate: byte-identical file + bit-exact round trip (every rank) -------------------
+    flen = ctx.compress_ptr(d_in.data_ptr(), n, d_file.data_ptr(), cap, device=True)
+    ctx.decompress_ptr(d_file.data_ptr(), flen, d_back.data_ptr(), n, device=True)
+    torch.cuda.synchronize()
+    if not torch.equal(d_back, d_in):
+        raise SystemExit("bench.py: round trip is not bit exact")
+    file_sha = hashlib.sha256(d_file[:flen].cpu().numpy().tobytes()).hexdigest()
+    golden_ok = None
+    if rank == 0 and n == N_TEXT:
+        g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))["text"][str(n)]
+        golden_ok = file_sha == g["sha256"]           # sha256 of the REAL reference's output for this input
+        if not golden_ok:
+            raise SystemExit("bench.py: compressed file differs from the reference golden")
+
+    def step_device():
+        fl = ctx.compress_ptr(d_in.data_ptr(), n, d_file.data_ptr(), cap, device=True)
+        sc = ctx.stats()
+        ctx.decompress_ptr(d_file.data_ptr(), fl, d_back.data_ptr(), n, device=True)
+        sd = ctx.stats()
+        return fl, sc, sd
+
+    def step_host():
+        fl = ctx.compress_ptr(h_in.data_ptr(), n, h_file.data_ptr(), cap, device=False)
+        ctx.decompress_ptr(h_file.data_ptr(), fl, h_back.data_ptr(), n, device=False)
+        return fl
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    # ---- timed region: device-resident ---------------------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = ctx.stats().kernel_launches
+    barrier()
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    agg = {"c_ms": 0.0, "d_ms": 0.0, "sort_ms": 0.0, "sort_bytes": 0, "passes": 0, "rounds": 0, "iters": 0,
+           "c_bwt": 0.0, "c_mtf": 0.0, "c_huf": 0.0, "d_huf": 0.0, "d_mtf": 0.0, "d_bwt": 0.0}
+    e0.record(stream)
+    for _ in range(args.steps):
+        fl, sc, sd = step_device()
+        agg["c_ms"] += sc.ms_total
+        agg["d_ms"] += sd.ms_total
+        agg["sort_ms"] += sc.ms_sort
+        agg["sort_bytes"] += sc.sort_bytes
+        agg["passes"] += sc.bwt_sort_passes
+        agg["rounds"] = sc.bwt_rounds
+        agg["iters"] = sd.decode_sync_iters
+        agg["c_bwt"] += sc.ms_bwt; agg["c_mtf"] += sc.ms_mtf; agg["c_huf"] += sc.ms_huffman
+        agg["d_huf"] += sd.ms_huffman; agg["d_mtf"] += sd.ms_mtf; agg["d_bwt"] += sd.ms_bwt
+    e1.record(stream)
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    launches = ctx.stats().kernel_launches - launches0
+    # ---- timed region: host buffers (e2e) ---------------------------------------------------------------
+    for _ in range(2):
+        step_host()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fl = step_host()
+    f1.record(stream)
+    barrier()
+    host_wall_ms = (time.perf_counter() - t0) * 1e3
+    host_ms = max(f0.elapsed_time(f1), host_wall_ms)
+    clocks = sampler.stop() if sampler else None
+    if not np.array_equal(h_back.numpy(), data):
+        raise SystemExit("bench.py: host round trip is not bit exact")
+
+    t = torch.tensor([dev_ms, host_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, host_ms = float(t[0]), float(t[1])
+    total_bytes = float(n) * world * args.steps
+    value = total_bytes / (dev_ms * 1e-3) / 1e6
+    e2e = total_bytes / (host_ms * 1e-3) / 1e6
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        K = args.steps
+        sort_gbs = agg["sort_bytes"] / (agg["sort_ms"] * 1e-3) / 1e9 if agg["sort_ms"] > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(dev_ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8 symbols / u32 ranks / u64 sort keys (integer only)", "data": "synthetic",
+            "config": {"workload": "text64m" if n == N_TEXT else "text%d" % n, "block_bytes": n, "blocks_per_step_per_gpu": 1,
+                       "generator": "book1 words, splitmix64 seed 0x5EED0064+rank (SURVEY 8d C3)",
+                       "l2": "working set (64 MiB input + 28 B/byte of sort state) larger than the 126 MB L2; no explicit flush",
+                       "parallelism": "independent files, one per GPU per step, no data-path collective" if world > 1 else "1 GPU"},
+            "compress_MBps": round(n * K / (agg["c_ms"] * 1e-3) / 1e6, 2),
+            "decompress_MBps": round(n * K / (agg["d_ms"] * 1e-3) / 1e6, 2),
+            "stage_ms_per_step": {"bwt": round(agg["c_bwt"] / K, 3), "mtf": round(agg["c_mtf"] / K, 3),
+                                  "hist+huffman_encode": round(agg["c_huf"] / K, 3),
+                                  "huffman_decode": round(agg["d_huf"] / K, 3), "imtf": round(agg["d_mtf"] / K, 3),
+                                  "ibwt": round(agg["d_bwt"] / K, 3)},
+            "compressed_bytes": int(fl), "file_sha256_matches_reference_golden": golden_ok,
+            "bwt_rounds": agg["rounds"], "decode_sync_iters": agg["iters"],
+            "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": int(n + fl), "d2h_bytes_per_step": int(fl + n),
+                    "ms_per_step": round(host_ms / K, 4)},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "onesweep_pass_kernel<u64 key, u32 payload> (BWT prefix-doubling sort pass)",
+                         "bound": "hbm", "achieved": round(sort_gbs, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(sort_gbs / peak, 4), "traffic": None, "peak_source": peak_src,
+                         "launches_per_step": agg["passes"] // K,
+                         "avg_launch_ms": round(agg["sort_ms"] / max(agg["passes"], 1), 4),
+                         "algorithmic_bytes_per_launch": int(agg["sort_bytes"] // max(agg["passes"], 1)),
+                         "share_of_step": round(agg["sort_ms"] / dev_ms, 4)},
+            "clocks": clocks,
+        }
+        prof = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(prof):
+            try:
+                line["roofline"]["traffic"] = json.load(open(prof)).get("onesweep_pass_u64_dram_bytes_per_launch")
+            except Exception:
+                pass
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(data)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------
+def ref_bins():
+    d = os.path.join(ROOT, "oracle", "_ref")
+    c, dd = os.path.join(d, "ref_compress"), os.path.join(d, "ref_decompress")
+    return (c, dd) if os.path.exists(c) and os.path.exists(dd) else None
+
+
+def time_reference_roundtrip(samples, workers):
+    """Runs the reference's compress + decompress on each sample (one fresh process per file, the
+    only mode whose bytes are defined -- SURVEY App. B), `workers` samples at a time.  Returns
+    (seconds, kind)."""
+    bins = ref_bins()
+    with tempfile.TemporaryDirectory() as tmp:
+        paths = []
+        for i, s in enumerate(samples):
+            p = os.path.join(tmp, "in%d" % i)
+            np.ascontiguousarray(s).tofile(p)
+            paths.append(p)
+        if bins:
+            def work(p):
+                subprocess.run([bins[0], p, p + ".bz"], check=True, stdout=subprocess.DEVNULL)
+                subprocess.run([bins[1], p + ".bz", p + ".out"], check=True, stdout=subprocess.DEVNULL)
+            kind = "reference"
+        else:
+            import oracle_lib as O
+
+            def work(p):
+                d = np.fromfile(p, dtype=np.uint8)
+                O.o_decompress(O.o_compress(d))
+            kind = "port"
+        t0 = time.perf_counter()
+        if workers <= 1:
+            for p in paths:
+                work(p)
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(workers) as ex:
+                list(ex.map(work, paths))
+        dt = time.perf_counter() - t0
+        if bins:
+            for p, s in zip(paths[:1], samples[:1]):
+                if not np.array_equal(np.fromfile(p + ".out", dtype=np.uint8), s):
+                    raise SystemExit("reference round trip failed")
+    return dt, kind
+
+
+def cpu_baseline(data):
+    """The reference's own CPU path on this box's host cores, single thread (it has no threading),
+    on the first 8 MiB of the same workload."""
+    sample = data[: 8 << 20]
+    dt, kind = time_reference_roundtrip([sample], 1)
+    return {"value": round(sample.size / dt / 1e6, 3), "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": "first 8 MiB of the text64m block, compress + decompress, one process, wall clock incl. file I/O"}
+
+
+def run_reference(args):
+    from bwt_mtf_huffman_compressor_b200 import workloads as W
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 32))
+    per = 2 << 20
+    # each step: `workers` independent 2 MiB slices of the text workload, one reference process each
+    # (the reference cannot split one block; file-level parallelism is all it offers)
+    samples = [W.synthetic_text(per, BASE_SEED + 1000 + i) for i in range(workers)]
+    for _ in range(min(args.warmup, 1)):
+        time_reference_roundtrip(samples, workers)
+    t = 0.0
+    kind = "reference"
+    for _ in range(args.steps):
+        dt, kind = time_reference_roundtrip(samples, workers)
+        t += dt
+    value = per * workers * args.steps / t / 1e6
+    sample = "%d x 2 MiB slices of the text generator per step, one reference process per slice, %d at a time" % (workers, workers)
+    line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": min(args.warmup, 1), "ms_per_step": round(t / args.steps * 1e3, 2), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "text64m", "block_bytes": N_TEXT, "note": "bounded sample, see cpu_baseline.sample"},
+            "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": workers, "kind": kind, "sample": sample},
+            "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=N_TEXT)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -74,6 +74,7 @@ extern "C" void bzap_ctx_destroy(bzap_ctx *c)
     if (c->arena) cudaFree(c->arena);
     if (c->mailbox) cudaFreeHost(c->mailbox);
     for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 128; ++i) if (c->sort_ev[i]) cudaEventDestroy(c->sort_ev[i]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -216,6 +217,9 @@ static int pipeline_compress(bzap_ctx *ctx, const u8 *d_in, size_t n, u8 **d_fil
 
 static void finish_stats(bzap_ctx *ctx)
 {
+    double ms_sort = 0;
+    for (int i = 0; i + 1 < ctx->sort_ev_used; i += 2) ms_sort += ev_ms(ctx->sort_ev[i], ctx->sort_ev[i + 1]);
+    ctx->stats.ms_sort = ms_sort;
     ctx->stats.ms_bwt = ev_ms(ctx->ev[0], ctx->ev[1]);
     ctx->stats.ms_mtf = ev_ms(ctx->ev[1], ctx->ev[2]);
     ctx->stats.ms_huffman = ev_ms(ctx->ev[2], ctx->ev[3]);

@@ -201,6 +201,10 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
     if (n64 == 0) return bzap_fail(ctx, BZAP_ERR_EMPTY, "empty input");
     if (n64 > BZAP_MAX_BLOCK) return bzap_fail(ctx, BZAP_ERR_TOO_LARGE, "block of %zu bytes", n64);
     const u32 n = (u32)n64;
+    ctx->sort_ev_used = 0;
+    ctx->stats.sort_bytes = 0;
+    ctx->stats.sort_elems = n;
+    ctx->stats.ms_sort = 0;
     SortBuffers sb;
     sb.keys[0] = arena_get<u64>(ctx, n);
     sb.keys[1] = arena_get<u64>(ctx, n);

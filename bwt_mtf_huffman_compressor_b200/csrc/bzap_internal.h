@@ -23,6 +23,9 @@ struct bzap_ctx {
     // small pinned host mailbox for flags / histograms coming back from the device
     u8 *mailbox = nullptr;               // 64 KiB pinned
     cudaEvent_t ev[8] = {};
+    // event pairs bracketing each run of back-to-back onesweep passes (roofline evidence)
+    cudaEvent_t sort_ev[128] = {};
+    int sort_ev_used = 0;
     bzap_stats stats = {};
     u64 launches = 0;
     char err[256] = {0};

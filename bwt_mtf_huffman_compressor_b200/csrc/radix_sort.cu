@@ -241,8 +241,18 @@ int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, int nbits, u32 *d_his
     }
     int cur = 0, run = 0;
     bool have_vals = !vals_are_iota;
+    bool timed = false;
     for (int p = 0; p < passes; ++p) {
         if (h_trivial[p]) continue;
+        if (!timed && ctx->sort_ev_used + 2 <= 128) {
+            cudaEvent_t &e0 = ctx->sort_ev[ctx->sort_ev_used], &e1 = ctx->sort_ev[ctx->sort_ev_used + 1];
+            if (!e0) CU(ctx, cudaEventCreate(&e0));
+            if (!e1) CU(ctx, cudaEventCreate(&e1));
+            CU(ctx, cudaEventRecord(e0, ctx->stream));
+            timed = true;
+        }
+        // algorithmic bytes: key 8 B read + 8 B written, payload 4 B written (+ 4 B read unless generated)
+        ctx->stats.sort_bytes += (u64)n * (have_vals ? 24 : 20);
         if (!have_vals)
             LAUNCH(ctx, k_iota, tiles, RS_BLOCK, smem, b->keys[cur], b->keys[cur ^ 1], (const u32 *)nullptr,
                    b->vals[cur ^ 1], n, 8 * p, d_offsets + p * 256, d_status + (size_t)p * status_words, d_ticket + p);
@@ -252,6 +262,10 @@ int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, int nbits, u32 *d_his
         have_vals = true;
         cur ^= 1;
         ++run;
+    }
+    if (timed) {
+        CU(ctx, cudaEventRecord(ctx->sort_ev[ctx->sort_ev_used + 1], ctx->stream));
+        ctx->sort_ev_used += 2;
     }
     CU(ctx, cudaGetLastError());
     *out_keys = b->keys[cur];

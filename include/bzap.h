@@ -64,7 +64,9 @@ typedef struct {
     uint32_t decode_sync_iters;             /* self-synchronisation iterations of the last decode */
     uint32_t reserved;
     uint64_t payload_bytes;
-    double ms_sort;                         /* time inside onesweep passes of the last forward BWT */
+    double ms_sort;                         /* CUDA-event time inside onesweep passes of the last forward BWT */
+    uint64_t sort_bytes;                    /* algorithmic bytes those passes moved (key+payload read+write) */
+    uint64_t sort_elems;                    /* elements per pass (N) */
 } bzap_stats;
 
 /* ---- context ------------------------------------------------------------------------------ */
