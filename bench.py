@@ -175,7 +175,7 @@ def run_ours(args):
         agg["d_ms"] += sd.ms_total
         agg["sort_ms"] += sc.ms_sort
         agg["sort_bytes"] += sc.sort_bytes
-        agg["passes"] += sc.bwt_sort_passes
+        agg["passes"] += sc.bwt_full_passes
         agg["rounds"] = sc.bwt_rounds
         agg["iters"] = sd.decode_sync_iters
         agg["c_bwt"] += sc.ms_bwt; agg["c_mtf"] += sc.ms_mtf; agg["c_huf"] += sc.ms_huffman
@@ -232,7 +232,7 @@ def run_ours(args):
             "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": int(n + fl), "d2h_bytes_per_step": int(fl + n),
                     "ms_per_step": round(host_ms / K, 4)},
             "gpu_launches": int(launches),
-            "roofline": {"kernel": "onesweep_pass_kernel<u64 key, u32 payload> (BWT prefix-doubling sort pass)",
+            "roofline": {"kernel": "onesweep_pass_kernel<u64 key, u32 payload> (BWT prefix-doubling sort pass over all N rotations)",
                          "bound": "hbm", "achieved": round(sort_gbs, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(sort_gbs / peak, 4), "traffic": None, "peak_source": peak_src,
                          "launches_per_step": agg["passes"] // K,

@@ -52,7 +52,7 @@ class Tree(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("ms_total", C.c_double), ("ms_bwt", C.c_double), ("ms_mtf", C.c_double), ("ms_huffman", C.c_double),
                 ("kernel_launches", C.c_uint64), ("bwt_rounds", C.c_uint32), ("bwt_sort_passes", C.c_uint32),
-                ("decode_sync_iters", C.c_uint32), ("reserved", C.c_uint32), ("payload_bytes", C.c_uint64),
+                ("decode_sync_iters", C.c_uint32), ("bwt_full_passes", C.c_uint32), ("payload_bytes", C.c_uint64),
                 ("ms_sort", C.c_double), ("sort_bytes", C.c_uint64), ("sort_elems", C.c_uint64)]
 
 

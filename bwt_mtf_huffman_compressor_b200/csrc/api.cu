@@ -145,7 +145,7 @@ void *arena_alloc(bzap_ctx *ctx, size_t bytes)
 size_t scratch_bytes_compress(size_t n)
 {
     // text, last column, mtf, file image | 2 x u64 keys, 2 x u32 payload, rank | sort + mtf tables
-    return 4 * (n + 1024) + 28 * n + sort_scratch_bytes((u32)n) + 2 * (n / 128 + 4096) * 1280 + (8u << 20);
+    return 4 * (n + 1024) + 33 * n + sort_scratch_bytes((u32)n) + 2 * (n / 128 + 4096) * 1280 + (8u << 20);
 }
 size_t scratch_bytes_decompress(size_t n, size_t payload)
 {

@@ -13,8 +13,13 @@
 // Termination: all ranks distinct, or k >= N, or a round that creates no new group (then the
 // partition is a fixed point of doubling: every longer prefix induces the same partition).
 //
-// Digit histograms for the sort passes are never computed from the keys: digit j of an 8-byte
-// window is a text byte, and digit j of either key half is a digit of a rank, so one byte
+// Two regimes.  FULL rounds sort all N rotations.  Once at most half of the rotations still sit
+// in a group of size > 1, ACTIVE rounds take over: only those rotations are re-keyed (their group
+// start r1 and a gathered rank[(i+k) mod N]), sorted, and written back inside their group's slot
+// range of the suffix array; singletons are final and never touched again.
+//
+// Digit histograms for the sort passes are never computed from the full keys: digit j of an
+// 8-byte window is a text byte, and digit j of either key half is a digit of a rank, so one byte
 // histogram (round 0) or the rank-digit histogram fused into the re-rank kernel serves all
 // eight passes.
 #include "device_common.cuh"
@@ -59,7 +64,7 @@ __global__ void bwt_spread_hist_kernel(const u32 *__restrict__ src, int src_rows
     for (int p = 0; p < 8; ++p) hist8[p * 256 + threadIdx.x] = src[(p % src_rows) * 256 + threadIdx.x];
 }
 
-// ---- doubling keys ---------------------------------------------------------------------------------
+// ---- doubling keys (full rounds) -----------------------------------------------------------------
 __global__ void __launch_bounds__(256) bwt_pair_keys_kernel(const u32 *__restrict__ rank, u32 n, u32 k, u64 *__restrict__ keys)
 {
     const u32 kk = k % n;
@@ -70,97 +75,297 @@ __global__ void __launch_bounds__(256) bwt_pair_keys_kernel(const u32 *__restric
     }
 }
 
-// ---- re-rank ---------------------------------------------------------------------------------------
-// sorted keys (+ payload = rotation start, nullptr = identity) -> rank[start] = sparse rank,
-// number of groups, and the 4 x 256 histogram of rank digits for the next round's passes.
+// ---- re-rank (full rounds) ---------------------------------------------------------------------------
+// sorted keys (+ payload = rotation start, nullptr = identity) -> rank[start] = sparse rank (text
+// order), rs[j] = the same rank in sorted order, number of groups, number of singleton groups, and
+// the 4 x 256 histogram of rank digits for the next round's passes.  Persistent blocks take tiles
+// by ticket so that the shared-memory histogram is flushed once per block, not once per tile.
 struct RrSmem {
-    u64 keys[RR_TILE + 1];
+    u64 keys[RR_TILE + 2];
     u32 r[RR_TILE];
     u32 hist[4][256];
     u32 tmp[40];
     u32 ticket;
     u32 tile_prefix;
-    u32 heads;
+    u32 heads, singles;
 };
 
 __global__ void __launch_bounds__(RR_BLOCK)
-bwt_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, u32 n, u32 *__restrict__ rank,
-                  u32 *hist4, u32 *groups, u64 *status, u32 *ticket)
+bwt_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, u32 n, u32 ntiles, u32 *__restrict__ rank,
+                  u32 *__restrict__ rs, u32 *hist4, u32 *counters /* [0]=groups [1]=singletons */, u64 *status,
+                  u32 *ticket)
 {
     __shared__ RrSmem S;
     const u32 tid = threadIdx.x;
-    const u32 tile = take_ticket(ticket, &S.ticket);
-    const u32 base = tile * RR_TILE;
     for (u32 i = tid; i < 4 * 256; i += RR_BLOCK) (&S.hist[0][0])[i] = 0;
-    if (tid == 0) {
-        S.keys[0] = base ? keys[base - 1] : 0;
-        S.heads = 0;
-    }
+    if (tid == 0) { S.heads = 0; S.singles = 0; }
+    while (true) {
+        const u32 tile = take_ticket(ticket, &S.ticket);
+        if (tile >= ntiles) break;
+        const u32 base = tile * RR_TILE;
+        if (tid == 0) {
+            S.keys[0] = base ? keys[base - 1] : 0;
+            S.keys[RR_TILE + 1] = base + RR_TILE < n ? keys[base + RR_TILE] : 0;
+        }
 #pragma unroll
-    for (int i = 0; i < RR_ITEMS; ++i) {
-        u32 o = tid + i * RR_BLOCK;
-        S.keys[o + 1] = base + o < n ? keys[base + o] : 0;
-    }
-    __syncthreads();
+        for (int i = 0; i < RR_ITEMS; ++i) {
+            u32 o = tid + i * RR_BLOCK;
+            S.keys[o + 1] = base + o < n ? keys[base + o] : 0;
+        }
+        __syncthreads();
 
-    // blocked: thread owns RR_ITEMS consecutive sorted positions
-    u32 loc[RR_ITEMS];
-    u32 cur = 0, nheads = 0;
+        // blocked: thread owns RR_ITEMS consecutive sorted positions
+        u32 loc[RR_ITEMS];
+        u32 cur = 0, nheads = 0, nsingle = 0;
 #pragma unroll
-    for (int i = 0; i < RR_ITEMS; ++i) {
-        u32 o = tid * RR_ITEMS + i;
-        u32 p = base + o;
-        bool head = p < n && (p == 0 || S.keys[o + 1] != S.keys[o]);
-        if (head) { cur = p; ++nheads; }
-        loc[i] = cur;
-    }
-    u32 total;
-    u32 tprefix = block_exclusive_max(cur, S.tmp, &total);
-    if (tid < 32) {
-        u64 x = lookback_exclusive(status, tile, (u64)total, OpMax());
-        if (tid == 0) S.tile_prefix = (u32)x;
-    }
-    if (nheads) atomicAdd(&S.heads, nheads);
-    __syncthreads();
-    const u32 pre = max(S.tile_prefix, tprefix);
+        for (int i = 0; i < RR_ITEMS; ++i) {
+            u32 o = tid * RR_ITEMS + i;
+            u32 p = base + o;
+            bool head = p < n && (p == 0 || S.keys[o + 1] != S.keys[o]);
+            bool next_head = p + 1 >= n || S.keys[o + 2] != S.keys[o + 1];
+            if (head) { cur = p; ++nheads; nsingle += next_head; }
+            loc[i] = cur;
+        }
+        u32 total;
+        u32 tprefix = block_exclusive_max(cur, S.tmp, &total);
+        if (tid < 32) {
+            u64 x = lookback_exclusive(status, tile, (u64)total, OpMax());
+            if (tid == 0) S.tile_prefix = (u32)x;
+        }
+        if (nheads) atomicAdd(&S.heads, nheads);
+        if (nsingle) atomicAdd(&S.singles, nsingle);
+        __syncthreads();
+        const u32 pre = max(S.tile_prefix, tprefix);
 
-    // ranks + run-aggregated digit histogram (ranks are non-decreasing along sorted order, so the
-    // high digits are almost constant inside a thread's run)
-    u32 run_d[4] = {0, 0, 0, 0}, run_c[4] = {0, 0, 0, 0};
+        // ranks + run-aggregated digit histogram (ranks are non-decreasing along sorted order, so
+        // the high digits are almost constant inside a thread's run)
+        u32 run_d[4] = {0, 0, 0, 0}, run_c[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int i = 0; i < RR_ITEMS; ++i) {
-        u32 o = tid * RR_ITEMS + i;
-        if (base + o < n) {
-            u32 r = max(pre, loc[i]);
-            S.r[o] = r;
+        for (int i = 0; i < RR_ITEMS; ++i) {
+            u32 o = tid * RR_ITEMS + i;
+            if (base + o < n) {
+                u32 r = max(pre, loc[i]);
+                S.r[o] = r;
 #pragma unroll
-            for (int d = 0; d < 4; ++d) {
-                u32 dig = (r >> (8 * d)) & 0xff;
-                if (run_c[d] && dig != run_d[d]) {
-                    atomicAdd(&S.hist[d][run_d[d]], run_c[d]);
-                    run_c[d] = 0;
+                for (int d = 0; d < 4; ++d) {
+                    u32 dig = (r >> (8 * d)) & 0xff;
+                    if (run_c[d] && dig != run_d[d]) {
+                        atomicAdd(&S.hist[d][run_d[d]], run_c[d]);
+                        run_c[d] = 0;
+                    }
+                    run_d[d] = dig;
+                    ++run_c[d];
                 }
-                run_d[d] = dig;
-                ++run_c[d];
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+            if (run_c[d]) atomicAdd(&S.hist[d][run_d[d]], run_c[d]);
+        __syncthreads();
+
+#pragma unroll
+        for (int i = 0; i < RR_ITEMS; ++i) {
+            u32 o = tid + i * RR_BLOCK;
+            u32 p = base + o;
+            if (p < n) {
+                u32 r = S.r[o];
+                rs[p] = r;
+                if (rank) rank[sa ? sa[p] : p] = r;          // nullptr: a bucketed scatter follows
             }
         }
     }
-#pragma unroll
-    for (int d = 0; d < 4; ++d)
-        if (run_c[d]) atomicAdd(&S.hist[d][run_d[d]], run_c[d]);
     __syncthreads();
-
-#pragma unroll
-    for (int i = 0; i < RR_ITEMS; ++i) {
-        u32 o = tid + i * RR_BLOCK;
-        u32 p = base + o;
-        if (p < n) rank[sa ? sa[p] : p] = S.r[o];
-    }
     for (u32 i = tid; i < 4 * 256; i += RR_BLOCK) {
         u32 c = (&S.hist[0][0])[i];
         if (c) atomicAdd(&hist4[i], c);
     }
-    if (tid == 0 && S.heads) atomicAdd(groups, S.heads);
+    if (tid == 0) {
+        if (S.heads) atomicAdd(&counters[0], S.heads);
+        if (S.singles) atomicAdd(&counters[1], S.singles);
+    }
+}
+
+// ---- active rounds -------------------------------------------------------------------------------------
+#define AC_BLOCK 256
+#define AC_ITEMS 4
+#define AC_TILE (AC_BLOCK * AC_ITEMS)
+
+// stable compaction helper: each thread brings `cnt` (0..AC_ITEMS) survivors; returns the global
+// output offset of the thread's first survivor (sum look-back over tiles)
+__device__ __forceinline__ u32 compact_offset(u32 cnt, u32 tile, u64 *status, u32 *s_tmp, u32 *s_base)
+{
+    u32 total;
+    u32 ex = block_exclusive_sum(cnt, s_tmp, &total);
+    if (threadIdx.x < 32) {
+        u64 x = lookback_exclusive(status, tile, (u64)total, OpSum());
+        if (threadIdx.x == 0) *s_base = (u32)x;
+    }
+    __syncthreads();
+    u32 r = *s_base + ex;
+    __syncthreads();
+    return r;
+}
+
+// after the last full round: sorted position j is settled iff its group is a singleton, i.e.
+// rs[j] == j and rs[j+1] == j+1.  Survivors keep their order: (start, group rank r1).
+__global__ void __launch_bounds__(AC_BLOCK)
+bwt_collect_active_kernel(const u32 *__restrict__ rs, const u32 *__restrict__ sa, u32 n, u32 *__restrict__ act_idx,
+                          u32 *__restrict__ act_r1, u64 *status, u32 *ticket)
+{
+    __shared__ u32 s_tmp[40];
+    __shared__ u32 s_ticket, s_base;
+    const u32 tile = take_ticket(ticket, &s_ticket);
+    const u32 j0 = tile * AC_TILE + threadIdx.x * AC_ITEMS;
+    u32 r[AC_ITEMS + 1];
+#pragma unroll
+    for (int i = 0; i <= AC_ITEMS; ++i) r[i] = j0 + i < n ? rs[j0 + i] : j0 + i;   // past the end counts as a head
+    bool keep[AC_ITEMS];
+    u32 cnt = 0;
+#pragma unroll
+    for (int i = 0; i < AC_ITEMS; ++i) {
+        u32 j = j0 + i;
+        keep[i] = j < n && !(r[i] == j && r[i + 1] == j + 1);
+        cnt += keep[i];
+    }
+    u32 o = compact_offset(cnt, tile, status, s_tmp, &s_base);
+#pragma unroll
+    for (int i = 0; i < AC_ITEMS; ++i)
+        if (keep[i]) {
+            act_idx[o] = sa ? sa[j0 + i] : j0 + i;
+            act_r1[o] = r[i];
+            ++o;
+        }
+}
+
+// key[a] = (r1 << 32) | rank[(start + k) mod N] with the eight digit histograms (M is small here)
+__global__ void __launch_bounds__(256)
+bwt_active_keys_kernel(const u32 *__restrict__ act_idx, const u32 *__restrict__ act_r1, u32 m, const u32 *__restrict__ rank,
+                       u32 n, u32 k, u64 *__restrict__ keys, u32 *hist8)
+{
+    __shared__ u32 s_h[8 * 256];
+    for (u32 i = threadIdx.x; i < 8 * 256; i += 256) s_h[i] = 0;
+    __syncthreads();
+    const u32 kk = k % n;
+    for (u32 a = blockIdx.x * blockDim.x + threadIdx.x; a < m; a += gridDim.x * blockDim.x) {
+        u32 j = act_idx[a] + kk;
+        if (j >= n) j -= n;
+        u64 key = ((u64)act_r1[a] << 32) | rank[j];
+        keys[a] = key;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) atomicAdd(&s_h[p * 256 + ((u32)(key >> (8 * p)) & 0xffu)], 1u);
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < 8 * 256; i += 256) {
+        u32 c = s_h[i];
+        if (c) atomicAdd(&hist8[i], c);
+    }
+}
+
+// sorted active (key, start) -> slot inside the group's range of the suffix array, new sparse rank.
+//   gstart[a] = index of the first active element with the same r1     (max-scan of group heads)
+//   pos[a]    = r1 + (a - gstart[a])                                     slot in the suffix array
+//   newr[a]   = pos of the first element with the same (r1, r2)         (max-scan of sub-group heads)
+// pos is strictly increasing in a, so both scans are max-scans of monotone values.
+__global__ void __launch_bounds__(AC_BLOCK)
+bwt_active_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ idx, u32 m, u32 *__restrict__ sa,
+                         u32 *__restrict__ rank, u32 *__restrict__ newr, u32 *__restrict__ pos_out,
+                         u32 *counters /* [0]=groups [1]=sub groups */, u64 *status_g, u64 *status_s, u32 *ticket)
+{
+    __shared__ u32 s_tmp[40];
+    __shared__ u32 s_ticket, s_pg, s_ps;
+    const u32 tile = take_ticket(ticket, &s_ticket);
+    const u32 a0 = tile * AC_TILE + threadIdx.x * AC_ITEMS;
+    u64 kcur[AC_ITEMS + 1];
+    kcur[0] = (a0 > 0 && a0 - 1 < m) ? keys[a0 - 1] : 0;
+#pragma unroll
+    for (int i = 0; i < AC_ITEMS; ++i) kcur[i + 1] = a0 + i < m ? keys[a0 + i] : 0;
+    // pass 1: group heads (r1 changes) -> gstart; the scan carries (index + 1), 0 = none yet
+    u32 gl[AC_ITEMS];
+    u32 gcur = 0, ng = 0;
+#pragma unroll
+    for (int i = 0; i < AC_ITEMS; ++i) {
+        u32 a = a0 + i;
+        bool gh = a < m && (a == 0 || (u32)(kcur[i + 1] >> 32) != (u32)(kcur[i] >> 32));
+        if (gh) { gcur = a + 1; ++ng; }
+        gl[i] = gcur;
+    }
+    u32 total;
+    u32 tpre = block_exclusive_max(gcur, s_tmp, &total);
+    if (threadIdx.x < 32) {
+        u64 x = lookback_exclusive(status_g, tile, (u64)total, OpMax());
+        if (threadIdx.x == 0) s_pg = (u32)x;
+    }
+    __syncthreads();
+    const u32 gpre = max(s_pg, tpre);
+    // pass 2: slots and sub-group heads -> new ranks; the scan carries (pos + 1)
+    u32 pos[AC_ITEMS], sl[AC_ITEMS];
+    u32 scur = 0, ns = 0;
+#pragma unroll
+    for (int i = 0; i < AC_ITEMS; ++i) {
+        u32 a = a0 + i;
+        u32 gs = max(gpre, gl[i]) - 1u;                      // index of the group's first active element
+        pos[i] = (u32)(kcur[i + 1] >> 32) + (a - gs);
+        bool sh = a < m && (a == 0 || kcur[i + 1] != kcur[i]);
+        if (sh) { scur = pos[i] + 1; ++ns; }
+        sl[i] = scur;
+    }
+    __syncthreads();
+    u32 tpre2 = block_exclusive_max(scur, s_tmp, &total);
+    if (threadIdx.x < 32) {
+        u64 x = lookback_exclusive(status_s, tile, (u64)total, OpMax());
+        if (threadIdx.x == 0) s_ps = (u32)x;
+    }
+    __syncthreads();
+    const u32 spre = max(s_ps, tpre2);
+#pragma unroll
+    for (int i = 0; i < AC_ITEMS; ++i) {
+        u32 a = a0 + i;
+        if (a < m) {
+            u32 nr = max(spre, sl[i]) - 1u;
+            u32 start = idx[a];
+            sa[pos[i]] = start;
+            rank[start] = nr;
+            newr[a] = nr;
+            pos_out[a] = pos[i];
+        }
+    }
+    if (ng) atomicAdd(&counters[0], ng);
+    if (ns) atomicAdd(&counters[1], ns);
+}
+
+// survivors of an active round: sub-groups that still have more than one member
+__global__ void __launch_bounds__(AC_BLOCK)
+bwt_active_compact_kernel(const u32 *__restrict__ newr, const u32 *__restrict__ pos, const u32 *__restrict__ idx, u32 m,
+                          u32 *__restrict__ out_idx, u32 *__restrict__ out_r1, u32 *count, u64 *status, u32 *ticket)
+{
+    __shared__ u32 s_tmp[40];
+    __shared__ u32 s_ticket, s_base;
+    const u32 tile = take_ticket(ticket, &s_ticket);
+    const u32 a0 = tile * AC_TILE + threadIdx.x * AC_ITEMS;
+    bool head[AC_ITEMS + 1];
+#pragma unroll
+    for (int i = 0; i <= AC_ITEMS; ++i) head[i] = a0 + i >= m || newr[a0 + i] == pos[a0 + i];
+    bool keep[AC_ITEMS];
+    u32 cnt = 0;
+#pragma unroll
+    for (int i = 0; i < AC_ITEMS; ++i) {
+        keep[i] = a0 + i < m && !(head[i] && head[i + 1]);
+        cnt += keep[i];
+    }
+    u32 o = compact_offset(cnt, tile, status, s_tmp, &s_base);
+    if (cnt) atomicAdd(count, cnt);
+#pragma unroll
+    for (int i = 0; i < AC_ITEMS; ++i)
+        if (keep[i]) {
+            out_idx[o] = idx[a0 + i];
+            out_r1[o] = newr[a0 + i];
+            ++o;
+        }
+}
+
+__global__ void iota_kernel(u32 *out, u32 n)
+{
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = i;
 }
 
 // ---- last column --------------------------------------------------------------------------------------
@@ -187,7 +392,6 @@ __global__ void __launch_bounds__(256) bwt_gather_kernel(const u8 *__restrict__ 
     }
 }
 
-
 // ---- host driver -----------------------------------------------------------------------------------------
 static inline u32 grid_for(size_t work_items, u32 per_block, u32 cap = 148u * 16u)
 {
@@ -203,6 +407,7 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
     const u32 n = (u32)n64;
     ctx->sort_ev_used = 0;
     ctx->stats.sort_bytes = 0;
+    ctx->stats.bwt_full_passes = 0;
     ctx->stats.sort_elems = n;
     ctx->stats.ms_sort = 0;
     SortBuffers sb;
@@ -211,15 +416,20 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
     sb.vals[0] = arena_get<u32>(ctx, n);
     sb.vals[1] = arena_get<u32>(ctx, n);
     u32 *d_rank = arena_get<u32>(ctx, n);
+    u32 *d_rs = arena_get<u32>(ctx, n);
     const u32 rr_tiles = (n + RR_TILE - 1) / RR_TILE;
-    // control: hist8[8*256] | hist4[4*256] groups ticket pad | status[rr_tiles] (u64)
+    const u32 ac_tiles_max = (n / 2 + AC_TILE) / AC_TILE + 1;
+    // control: hist8[8*256] | hist4[4*256] counters[4] ticket pad | status (u64)
     u32 *d_hist8 = arena_get<u32>(ctx, 8 * 256);
-    u32 *d_rrctl = arena_get<u32>(ctx, 4 * 256 + 8 + 2 * (size_t)rr_tiles);
-    if (!sb.keys[0] || !sb.keys[1] || !sb.vals[0] || !sb.vals[1] || !d_rank || !d_hist8 || !d_rrctl)
+    const size_t status_u64 = (size_t)(rr_tiles > 2 * ac_tiles_max ? rr_tiles : 2 * ac_tiles_max) + 8;
+    u32 *d_rrctl = arena_get<u32>(ctx, 4 * 256 + 8 + 2 * status_u64);
+    const u32 ctiles = (n + AC_TILE - 1) / AC_TILE;
+    u64 *cstatus = arena_get<u64>(ctx, (size_t)ctiles + 4);
+    if (!sb.keys[0] || !sb.keys[1] || !sb.vals[0] || !sb.vals[1] || !d_rank || !d_rs || !d_hist8 || !d_rrctl || !cstatus)
         return bzap_fail(ctx, BZAP_ERR_NOMEM, "bwt scratch");
-    u32 *d_hist4 = d_rrctl, *d_groups = d_rrctl + 4 * 256, *d_ticket = d_groups + 1;
+    u32 *d_hist4 = d_rrctl, *d_counters = d_rrctl + 4 * 256, *d_ticket = d_counters + 4;
     u64 *d_status = (u64 *)(d_rrctl + 4 * 256 + 8);
-    const size_t rrctl_bytes = (4 * 256 + 8 + 2 * (size_t)rr_tiles) * sizeof(u32);
+    const size_t rrctl_bytes = (4 * 256 + 8 + 2 * status_u64) * sizeof(u32);
     const size_t arena_mark = ctx->arena_off;
 
     // round 0: byte histogram stands in for all eight digit histograms of the 8-byte windows
@@ -232,27 +442,91 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
     u32 *sa = nullptr;
     u32 rounds = 0, passes_total = 0, prev_groups = 0;
     u64 k = 8;
-    u32 *h_groups = (u32 *)(ctx->mailbox + 1024);
+    u32 *h_cnt = (u32 *)(ctx->mailbox + 1024);
+    bool finished = false;
+    u32 active = n;
+    // ---- full rounds ----
     while (true) {
         int passes = 0;
         ctx->arena_off = arena_mark;             // sort control block is per round
         RET(dev_sort_pairs64(ctx, &sb, n, 64, d_hist8, true, &keys, &sa, &passes));
         passes_total += (u32)passes;
         CU(ctx, cudaMemsetAsync(d_rrctl, 0, rrctl_bytes, ctx->stream));
-        LAUNCH(ctx, bwt_rerank_kernel, rr_tiles, RR_BLOCK, 0, keys, sa, n, d_rank, d_hist4, d_groups, d_status, d_ticket);
-        CU(ctx, cudaMemcpyAsync(h_groups, d_groups, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        // rank[] is larger than L2 for big blocks: scatter it through a bucketing pass (radix_sort.cu)
+        const bool bucketed = sa != nullptr && n > (12u << 20);
+        LAUNCH(ctx, bwt_rerank_kernel, grid_for(rr_tiles, 1, 148 * 6), RR_BLOCK, 0, keys, sa, n, rr_tiles,
+               bucketed ? (u32 *)nullptr : d_rank, d_rs, d_hist4, d_counters, d_status, d_ticket);
+        if (bucketed) RET(dev_scatter_perm(ctx, sa, d_rs, n, d_rank, (u32 *)keys, (u32 *)keys + n));
+        CU(ctx, cudaMemcpyAsync(h_cnt, d_counters, 2 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         ++rounds;
-        const u32 groups = *h_groups;
-        if (groups == n || k >= n || groups == prev_groups) break;
+        const u32 groups = h_cnt[0];
+        active = n - h_cnt[1];
+        if (groups == n || k >= n || groups == prev_groups) { finished = true; break; }
         prev_groups = groups;
+        if (active <= n / 2) break;              // few rotations left unsettled: switch regime
         LAUNCH(ctx, bwt_spread_hist_kernel, 1, 256, 0, d_hist4, 4, d_hist8);
         // keys always rebuilt into buffer 0 in text order; payload = identity again
         LAUNCH(ctx, bwt_pair_keys_kernel, grid_for(n, 256 * 4), 256, 0, d_rank, n, (u32)(k % n), sb.keys[0]);
         k *= 2;
     }
+    // ---- active rounds ----
+    if (!finished) {
+        // suffix array lives in the payload buffer the last sort ended in (materialise an identity one)
+        u32 *sa_buf = sa;
+        if (!sa_buf) {
+            sa_buf = sb.vals[0];
+            LAUNCH(ctx, iota_kernel, grid_for(n, 256 * 4), 256, 0, sa_buf, n);
+        }
+        u32 *other_vals = sa_buf == sb.vals[0] ? sb.vals[1] : sb.vals[0];
+        // M <= n/2 elements: both key buffers fit into keys[0], both payload buffers into the free
+        // payload array, and the four per-element u32 arrays into keys[1]
+        const u32 half = n / 2;                                // m <= n/2
+        SortBuffers ab;
+        ab.keys[0] = sb.keys[0];
+        ab.keys[1] = sb.keys[0] + half;
+        ab.vals[0] = other_vals;
+        ab.vals[1] = other_vals + half;
+        u32 *scratch = (u32 *)sb.keys[1];
+        u32 *act_r1 = scratch, *newr = scratch + half, *pos = scratch + 2 * (size_t)half;
+        u32 *next_idx = d_rs;                                  // rs is dead once the survivors are collected
+        u32 *next_r1 = d_rs + half;
+        u32 m = active;
+        CU(ctx, cudaMemsetAsync(d_rrctl, 0, rrctl_bytes, ctx->stream));
+        CU(ctx, cudaMemsetAsync(cstatus, 0, ((size_t)ctiles + 2) * sizeof(u64), ctx->stream));
+        LAUNCH(ctx, bwt_collect_active_kernel, ctiles, AC_BLOCK, 0, d_rs, sa, n, ab.vals[0], act_r1, cstatus, d_ticket);
+        while (true) {
+            const u32 mt = (m + AC_TILE - 1) / AC_TILE;
+            CU(ctx, cudaMemsetAsync(d_hist8, 0, 8 * 256 * sizeof(u32), ctx->stream));
+            LAUNCH(ctx, bwt_active_keys_kernel, grid_for(m, 256, 148 * 4), 256, 0, ab.vals[0], act_r1, m, d_rank, n,
+                   (u32)(k % n), ab.keys[0], d_hist8);
+            int passes = 0;
+            u64 *skeys = nullptr;
+            u32 *sidx = nullptr;
+            ctx->arena_off = arena_mark;
+            RET(dev_sort_pairs64(ctx, &ab, m, 64, d_hist8, false, &skeys, &sidx, &passes));
+            passes_total += (u32)passes;
+            CU(ctx, cudaMemsetAsync(d_rrctl, 0, rrctl_bytes, ctx->stream));
+            LAUNCH(ctx, bwt_active_rerank_kernel, mt, AC_BLOCK, 0, skeys, sidx, m, sa_buf, d_rank, newr, pos, d_counters,
+                   d_status, d_status + mt + 2, d_ticket);
+            CU(ctx, cudaMemsetAsync(cstatus, 0, ((size_t)mt + 2) * sizeof(u64), ctx->stream));
+            LAUNCH(ctx, bwt_active_compact_kernel, mt, AC_BLOCK, 0, newr, pos, sidx, m, next_idx, next_r1, d_counters + 2,
+                   cstatus, d_ticket + 1);
+            CU(ctx, cudaMemcpyAsync(h_cnt, d_counters, 3 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            ++rounds;
+            k *= 2;
+            const u32 groups = h_cnt[0], subgroups = h_cnt[1], m2 = h_cnt[2];
+            if (m2 == 0 || k >= n || subgroups == groups) break;
+            // survivors become the next round's input (copy into the sort's payload buffer 0)
+            CU(ctx, cudaMemcpyAsync(ab.vals[0], next_idx, (size_t)m2 * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+            CU(ctx, cudaMemcpyAsync(act_r1, next_r1, (size_t)m2 * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+            m = m2;
+        }
+        sa = sa_buf;
+    }
     LAUNCH(ctx, bwt_gather_kernel, grid_for((n + 3) / 4, 256), 256, 0, d_in, sa, n, d_last);
-    u32 *h_primary = (u32 *)(ctx->mailbox + 1032);
+    u32 *h_primary = (u32 *)(ctx->mailbox + 1040);
     CU(ctx, cudaMemcpyAsync(h_primary, d_rank, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaGetLastError());

@@ -123,3 +123,6 @@ int dev_sort_positions_by_byte(bzap_ctx *ctx, const u8 *d_bytes, u32 n, u32 *d_T
 size_t sort_scratch_bytes(u32 n);
 // 256-bin byte histogram accumulated into d_hist256 (caller zeroes it)
 int dev_byte_hist(bzap_ctx *ctx, const u8 *d_bytes, u32 n, u32 *d_hist256);
+// out[perm[j]] = vals[j] for a permutation perm of 0..n-1; tmp buffers hold n u32 each
+int dev_scatter_perm(bzap_ctx *ctx, const u32 *d_perm, const u32 *d_vals, u32 n, u32 *d_out, u32 *d_tmp_idx,
+                     u32 *d_tmp_vals);

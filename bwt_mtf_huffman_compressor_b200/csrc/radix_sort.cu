@@ -36,7 +36,7 @@ template <typename KeyT> __device__ __forceinline__ u32 digit_of(KeyT k, int shi
 
 // offsets = exclusive global digit offsets of this pass (256); status = tiles*256 zeroed words
 template <typename KeyT, int ITEMS, bool IOTA_VALS, bool WRITE_KEYS>
-__global__ void __launch_bounds__(RS_BLOCK)
+__global__ void __launch_bounds__(RS_BLOCK, 3)
 onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out, const u32 *__restrict__ vals_in,
                      u32 *__restrict__ vals_out, u32 n, int shift, const u32 *__restrict__ offsets, u32 *status,
                      u32 *ticket)
@@ -51,18 +51,11 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
     const u32 wbase = tile_base + warp * (32u * ITEMS);
 
     KeyT key[ITEMS];
-    u32 val[ITEMS];
     u32 rnk[ITEMS];
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         u32 idx = wbase + j * 32u + lane;
         key[j] = idx < n ? keys_in[idx] : (KeyT)~(KeyT)0;
-    }
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-        u32 idx = wbase + j * 32u + lane;
-        if (IOTA_VALS) val[j] = idx;
-        else val[j] = idx < n ? vals_in[idx] : 0u;
     }
     for (u32 i = lane; i < 256; i += 32) S.whist[warp][i] = 0;
     __syncwarp();
@@ -120,26 +113,41 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
     }
     __syncthreads();
 
-    // regroup by digit in shared memory
+    // regroup keys by digit in shared memory; rnk[] becomes the position inside the sorted tile
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
-        u32 d = digit_of(key[j], shift);
-        u32 pos = wh[d] + rnk[j];
+        u32 pos = wh[digit_of(key[j], shift)] + rnk[j];
         S.keys[pos] = key[j];
-        S.vals[pos] = val[j];
+        rnk[j] = pos;
+    }
+    // payload loads are issued only now (the key registers are dead) and fly during the key write-out
+    u32 val[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        u32 idx = wbase + j * 32u + lane;
+        if (IOTA_VALS) val[j] = idx;
+        else val[j] = idx < n ? vals_in[idx] : 0u;
     }
     __syncthreads();
 
     // contiguous per-digit runs go out; padding keys (digit 255, highest tile index) sit last
+    if (WRITE_KEYS) {
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            u32 idx = tid + i * RS_BLOCK;
+            if (idx < valid) {
+                KeyT k = S.keys[idx];
+                keys_out[S.adj[digit_of(k, shift)] + idx] = k;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) S.vals[rnk[j]] = val[j];
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         u32 idx = tid + i * RS_BLOCK;
-        if (idx < valid) {
-            KeyT k = S.keys[idx];
-            u32 g = S.adj[digit_of(k, shift)] + idx;
-            if (WRITE_KEYS) keys_out[g] = k;
-            vals_out[g] = S.vals[idx];
-        }
+        if (idx < valid) vals_out[S.adj[digit_of(S.keys[idx], shift)] + idx] = S.vals[idx];
     }
 }
 
@@ -244,7 +252,8 @@ int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, int nbits, u32 *d_his
     bool timed = false;
     for (int p = 0; p < passes; ++p) {
         if (h_trivial[p]) continue;
-        if (!timed && ctx->sort_ev_used + 2 <= 128) {
+        const bool full = (u64)n == ctx->stats.sort_elems;   // roofline evidence: full-size passes only
+        if (full && !timed && ctx->sort_ev_used + 2 <= 128) {
             cudaEvent_t &e0 = ctx->sort_ev[ctx->sort_ev_used], &e1 = ctx->sort_ev[ctx->sort_ev_used + 1];
             if (!e0) CU(ctx, cudaEventCreate(&e0));
             if (!e1) CU(ctx, cudaEventCreate(&e1));
@@ -252,7 +261,7 @@ int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, int nbits, u32 *d_his
             timed = true;
         }
         // algorithmic bytes: key 8 B read + 8 B written, payload 4 B written (+ 4 B read unless generated)
-        ctx->stats.sort_bytes += (u64)n * (have_vals ? 24 : 20);
+        if (full) { ctx->stats.sort_bytes += (u64)n * (have_vals ? 24 : 20); ++ctx->stats.bwt_full_passes; }
         if (!have_vals)
             LAUNCH(ctx, k_iota, tiles, RS_BLOCK, smem, b->keys[cur], b->keys[cur ^ 1], (const u32 *)nullptr,
                    b->vals[cur ^ 1], n, 8 * p, d_offsets + p * 256, d_status + (size_t)p * status_words, d_ticket + p);
@@ -302,6 +311,53 @@ int dev_sort_positions_by_byte(bzap_ctx *ctx, const u8 *d_bytes, u32 n, u32 *d_T
     }
     LAUNCH(ctx, k, tiles, RS_BLOCK, smem, d_bytes, (u8 *)nullptr, (const u32 *)nullptr, d_T, n, 0, d_cum, d_status,
            d_ticket);
+    CU(ctx, cudaGetLastError());
+    return BZAP_OK;
+}
+
+// ---- permutation scatter: out[perm[j]] = vals[j] ------------------------------------------------------------
+// A direct scatter of 4-byte words over an array larger than L2 costs a 32-byte sector read AND
+// write per element.  Instead: one onesweep pass buckets (perm, val) by the TOP 8 bits of the
+// target index (perm is a permutation of 0..n-1, so the digit histogram is known in closed form),
+// after which consecutive elements target one n/256-entry window that stays L2 resident and every
+// sector is written back exactly once.
+__global__ void perm_offsets_kernel(u32 n, int shift, u32 *offsets)
+{
+    u64 d = threadIdx.x;
+    u64 lo = d << shift;
+    offsets[threadIdx.x] = (u32)(lo < n ? lo : n);
+}
+
+__global__ void __launch_bounds__(256)
+scatter_u32_kernel(const u32 *__restrict__ idx, const u32 *__restrict__ vals, u32 n, u32 *__restrict__ out)
+{
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) out[idx[j]] = vals[j];
+}
+
+int dev_scatter_perm(bzap_ctx *ctx, const u32 *d_perm, const u32 *d_vals, u32 n, u32 *d_out, u32 *d_tmp_idx,
+                     u32 *d_tmp_vals)
+{
+    const u32 sgrid = min((n + 1023) / 1024, 148u * 16u);
+    if (n <= (12u << 20)) {                      // target array fits L2 comfortably: scatter directly
+        LAUNCH(ctx, scatter_u32_kernel, sgrid, 256, 0, d_perm, d_vals, n, d_out);
+        return BZAP_OK;
+    }
+    constexpr int ITEMS = 16;
+    const u32 tiles = (n + RS_BLOCK * ITEMS - 1) / (RS_BLOCK * ITEMS);
+    const size_t status_words = (size_t)tiles * 256;
+    u32 *d_ctl = arena_get<u32>(ctx, 256 + 8 + status_words);
+    if (!d_ctl) return bzap_fail(ctx, BZAP_ERR_NOMEM, "scatter scratch");
+    u32 *d_offsets = d_ctl, *d_ticket = d_ctl + 256, *d_status = d_ctl + 264;
+    CU(ctx, cudaMemsetAsync(d_ticket, 0, (8 + status_words) * sizeof(u32), ctx->stream));
+    int bits = 0;
+    while (((u64)1 << bits) < n) ++bits;          // n <= 2^bits
+    const int shift = bits > 8 ? bits - 8 : 0;
+    LAUNCH(ctx, perm_offsets_kernel, 1, 256, 0, n, shift, d_offsets);
+    auto k = onesweep_pass_kernel<u32, ITEMS, false, true>;
+    const size_t smem = sizeof(RsSmem<u32, ITEMS>);
+    RET(set_smem_attr(ctx, k, smem));
+    LAUNCH(ctx, k, tiles, RS_BLOCK, smem, d_perm, d_tmp_idx, d_vals, d_tmp_vals, n, shift, d_offsets, d_status, d_ticket);
+    LAUNCH(ctx, scatter_u32_kernel, sgrid, 256, 0, d_tmp_idx, d_tmp_vals, n, d_out);
     CU(ctx, cudaGetLastError());
     return BZAP_OK;
 }

@@ -62,7 +62,7 @@ typedef struct {
     uint32_t bwt_rounds;                    /* prefix-doubling rounds of the last forward BWT   */
     uint32_t bwt_sort_passes;               /* onesweep passes executed in the last forward BWT */
     uint32_t decode_sync_iters;             /* self-synchronisation iterations of the last decode */
-    uint32_t reserved;
+    uint32_t bwt_full_passes;               /* ... of which over all N rotations (timed: ms_sort / sort_bytes) */
     uint64_t payload_bytes;
     double ms_sort;                         /* CUDA-event time inside onesweep passes of the last forward BWT */
     uint64_t sort_bytes;                    /* algorithmic bytes those passes moved (key+payload read+write) */

@@ -64,6 +64,29 @@ def test_bwt_degenerate(kind, n):
     assert_same(last, ol, kind)
 
 
+def test_bwt_active_rounds():
+    # inputs that leave the "all rotations" regime early and then need many rounds on a small
+    # active set: long repeats inside random data, half-periodic blocks, a run at the end
+    rng = np.random.default_rng(21)
+    base = rng.integers(0, 256, 300000, dtype=np.uint8)
+    rep = base.copy()
+    rep[200000:250000] = rep[50000:100000]              # one 50 KB repeat (LCP up to 50000)
+    rep[260000:270000] = rep[50000:60000]
+    cases = {
+        "long_repeat": rep,
+        "random_then_ab": np.concatenate([rng.integers(0, 256, 60000, dtype=np.uint8), W.degenerate("ab", 40000)]),
+        "random_then_zeros": np.concatenate([rng.integers(0, 256, 70001, dtype=np.uint8), np.zeros(29999, dtype=np.uint8)]),
+        "two_copies_plus_one": np.concatenate([base[:100000], base[:100000], base[:1]]),
+        "text_with_dup": np.concatenate([W.synthetic_text(200000), W.synthetic_text(200000)[:150000]]),
+        "small_alphabet": rng.integers(0, 2, 200000, dtype=np.uint8),
+    }
+    for name, d in cases.items():
+        p, last = bz.bwt(d)
+        ol, op = O.o_bwt(d)
+        assert p == op, "%s primary %d want %d" % (name, p, op)
+        assert_same(last, ol, name)
+
+
 def mtf_inputs(calgary):
     out = {k: np.frombuffer(v, dtype=np.uint8) for k, v in SMALL.items()}
     for name in ["obj1", "geo", "book1", "pic"]:

@@ -1,0 +1,26 @@
+#!/usr/bin/env python
+"""Prints the key metrics of an .ncu-rep (raw page) per captured launch."""
+import csv, subprocess, sys
+rep = sys.argv[1]
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+hdr, units = rows[0], rows[1]
+want = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size', 'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+        'smsp__inst_executed.sum', 'lts__t_sector_hit_rate.pct', 'lts__t_sectors_op_write.sum', 'lts__t_sectors_op_read.sum','lts__t_sectors_op_atom.sum','lts__t_sectors_op_red.sum',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active']
+stalls = [h for h in hdr if h.startswith('smsp__average_warps_issue_stalled') and h.endswith('_per_issue_active.ratio')]
+for w in want + stalls:
+    if w in hdr:
+        i = hdr.index(w)
+        vals = [r[i][:48] for r in rows[2:]]
+        if w in stalls:
+            try:
+                if max(float(v) for v in vals) < 0.5:
+                    continue
+            except ValueError:
+                pass
+            w = w.replace('smsp__average_warps_issue_stalled_', 'stall_').replace('_per_issue_active.ratio', '')
+        print("%-60s %-8s %s" % (w[:60], units[i][:8], vals))
