@@ -13,7 +13,8 @@ reference's golden bytes and the round trip is bit exact (checked during warm-up
   e2e   : same through the host-buffer C ABI (bzap_compress / bzap_decompress) from pinned host
           memory, H2D and D2H copies inside the timed region
 N > 1: independent files, one per rank per step, no collective on the data path (weak scaling).
-Other workloads (--workload calgary | degenerate) are reported as extra lines on stderr only.
+The Calgary batch (BASELINE config 2) is measured after the timed region and reported under
+"calgary_batch" on the same line.
 """
 import argparse
 import hashlib
@@ -201,6 +202,8 @@ def run_ours(args):
     if not np.array_equal(h_back.numpy(), data):
         raise SystemExit("bench.py: host round trip is not bit exact")
 
+    cal = calgary_batch(bz, W, rank, world, dist)
+
     t = torch.tensor([dev_ms, host_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -240,6 +243,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": int(agg["sort_bytes"] // max(agg["passes"], 1)),
                          "share_of_step": round(agg["sort_ms"] / dev_ms, 4)},
             "clocks": clocks,
+            "calgary_batch": cal,
         }
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(prof):
@@ -252,6 +256,45 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def calgary_batch(bz, W, rank, world, dist):
+    """BASELINE config 2: the 14 Calgary files (3,141,622 B, one BWT block each) as a batch through
+    the host-buffer ABI (bzap_compress_batch: 8 streams per GPU; files sharded over ranks when
+    N > 1).  Latency bound on a B200; reported beside the headline, not part of `value`."""
+    import torch
+    from bwt_mtf_huffman_compressor_b200 import sharding
+    cal = W.calgary()
+    names = W.CALGARY_FILES
+    sizes = [len(cal[n]) for n in names]
+    mine = sharding.shard_files(sizes, world)[rank]
+    datas = [np.frombuffer(cal[names[i]], dtype=np.uint8) for i in mine]
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))["calgary"]
+    ok = True
+    blobs = []
+    tc = td = 0.0
+    reps = 5
+    for it in range(reps + 2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        blobs = bz.compress_batch(datas, 8) if datas else []
+        t1 = time.perf_counter()
+        outs = bz.decompress_batch(blobs, 8) if blobs else []
+        t2 = time.perf_counter()
+        if it >= 2:
+            tc += t1 - t0
+            td += t2 - t1
+        if it == 0:
+            for i, b, o in zip(mine, blobs, outs):
+                ok = ok and hashlib.sha256(b.tobytes()).hexdigest() == g[names[i]]["sha256"] and o.tobytes() == cal[names[i]]
+    tc = sharding.max_over_ranks(tc, dist, "cuda")
+    td = sharding.max_over_ranks(td, dist, "cuda")
+    ok = sharding.max_over_ranks(0.0 if ok else 1.0, dist, "cuda") == 0.0
+    total = float(sum(sizes)) * reps
+    return {"files": len(names), "bytes": int(sum(sizes)), "streams_per_gpu": 8,
+            "compress_MBps": round(total / tc / 1e6, 1), "decompress_MBps": round(total / td / 1e6, 1),
+            "roundtrip_MBps": round(total / (tc + td) / 1e6, 1), "byte_identical_to_reference_goldens": bool(ok),
+            "timing": "host wall clock incl. H2D/D2H, max over ranks"}
 
 
 # ---------------------------------------------------------------------------------------------------
