@@ -32,15 +32,17 @@
 #define IK_BLOCK 256
 #define IK_ITEMS 8
 #define IK_TILE (IK_BLOCK * IK_ITEMS)
-__global__ void __launch_bounds__(IK_BLOCK) bwt_init_keys_kernel(const u8 *__restrict__ text, u32 n, u64 *__restrict__ keys)
+// keys[i] for rotations lo .. lo+m-1 of an n-byte text (lo = 0, m = n on a single GPU)
+__global__ void __launch_bounds__(IK_BLOCK)
+bwt_init_keys_kernel(const u8 *__restrict__ text, u32 n, u32 lo, u32 m, u64 *__restrict__ keys)
 {
     __shared__ u8 s_b[IK_TILE + 8];
-    const u32 tiles = (n + IK_TILE - 1) / IK_TILE;
+    const u32 tiles = (m + IK_TILE - 1) / IK_TILE;
     for (u32 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const u32 base = tile * IK_TILE;
         __syncthreads();
         for (u32 i = threadIdx.x; i < IK_TILE + 8; i += IK_BLOCK) {
-            u64 p = (u64)base + i;
+            u64 p = (u64)lo + base + i;
             if (p >= n) p %= n;                   // cyclic window (main.cpp:38-44)
             s_b[i] = text[p];
         }
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(IK_BLOCK) bwt_init_keys_kernel(const u8 *__res
 #pragma unroll
         for (int i = 0; i < IK_ITEMS; ++i) {
             u32 o = threadIdx.x + i * IK_BLOCK;
-            if (base + o < n) {
+            if (base + o < m) {
                 u64 k = 0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) k = (k << 8) | s_b[o + j];
@@ -91,7 +93,8 @@ struct RrSmem {
 };
 
 __global__ void __launch_bounds__(RR_BLOCK)
-bwt_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, u32 n, u32 ntiles, u32 *__restrict__ rank,
+bwt_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, u32 n, u32 ntiles, u32 pos_base,
+                  u32 *__restrict__ rank,
                   u32 *__restrict__ rs, u32 *hist4, u32 *counters /* [0]=groups [1]=singletons */, u64 *status,
                   u32 *ticket)
 {
@@ -99,20 +102,30 @@ bwt_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, u32 
     const u32 tid = threadIdx.x;
     for (u32 i = tid; i < 4 * 256; i += RR_BLOCK) (&S.hist[0][0])[i] = 0;
     if (tid == 0) { S.heads = 0; S.singles = 0; }
-    while (true) {
-        const u32 tile = take_ticket(ticket, &S.ticket);
-        if (tile >= ntiles) break;
-        const u32 base = tile * RR_TILE;
-        if (tid == 0) {
-            S.keys[0] = base ? keys[base - 1] : 0;
-            S.keys[RR_TILE + 1] = base + RR_TILE < n ? keys[base + RR_TILE] : 0;
-        }
+    // software pipeline: the next tile's keys are in flight while the current tile is processed
+    u64 kreg[RR_ITEMS], kprev = 0, knext = 0;
+    auto fetch = [&](u32 t) {
+        if (t >= ntiles) return;
+        const u32 b = t * RR_TILE;
 #pragma unroll
         for (int i = 0; i < RR_ITEMS; ++i) {
             u32 o = tid + i * RR_BLOCK;
-            S.keys[o + 1] = base + o < n ? keys[base + o] : 0;
+            kreg[i] = b + o < n ? keys[b + o] : 0;
         }
-        __syncthreads();
+        if (tid == 0) {
+            kprev = b ? keys[b - 1] : 0;
+            knext = b + RR_TILE < n ? keys[b + RR_TILE] : 0;
+        }
+    };
+    u32 tile = take_ticket(ticket, &S.ticket);
+    fetch(tile);
+    while (tile < ntiles) {
+        const u32 base = tile * RR_TILE;
+#pragma unroll
+        for (int i = 0; i < RR_ITEMS; ++i) S.keys[tid + i * RR_BLOCK + 1] = kreg[i];
+        if (tid == 0) { S.keys[0] = kprev; S.keys[RR_TILE + 1] = knext; }
+        const u32 next_tile = take_ticket(ticket, &S.ticket);     // (barriers inside publish S.keys)
+        fetch(next_tile);
 
         // blocked: thread owns RR_ITEMS consecutive sorted positions
         u32 loc[RR_ITEMS];
@@ -123,7 +136,7 @@ bwt_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, u32 
             u32 p = base + o;
             bool head = p < n && (p == 0 || S.keys[o + 1] != S.keys[o]);
             bool next_head = p + 1 >= n || S.keys[o + 2] != S.keys[o + 1];
-            if (head) { cur = p; ++nheads; nsingle += next_head; }
+            if (head) { cur = pos_base + p; ++nheads; nsingle += next_head; }
             loc[i] = cur;
         }
         u32 total;
@@ -173,6 +186,7 @@ bwt_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, u32 
                 if (rank) rank[sa ? sa[p] : p] = r;          // nullptr: a bucketed scatter follows
             }
         }
+        tile = next_tile;
     }
     __syncthreads();
     for (u32 i = tid; i < 4 * 256; i += RR_BLOCK) {
@@ -436,7 +450,7 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
     CU(ctx, cudaMemsetAsync(d_hist4, 0, 256 * sizeof(u32), ctx->stream));
     RET(dev_byte_hist(ctx, d_in, n, d_hist4));
     LAUNCH(ctx, bwt_spread_hist_kernel, 1, 256, 0, d_hist4, 1, d_hist8);
-    LAUNCH(ctx, bwt_init_keys_kernel, grid_for((n + IK_TILE - 1) / IK_TILE, 1, 148 * 8), IK_BLOCK, 0, d_in, n, sb.keys[0]);
+    LAUNCH(ctx, bwt_init_keys_kernel, grid_for((n + IK_TILE - 1) / IK_TILE, 1, 148 * 8), IK_BLOCK, 0, d_in, n, 0u, n, sb.keys[0]);
 
     u64 *keys = nullptr;
     u32 *sa = nullptr;
@@ -454,7 +468,7 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
         CU(ctx, cudaMemsetAsync(d_rrctl, 0, rrctl_bytes, ctx->stream));
         // rank[] is larger than L2 for big blocks: scatter it through a bucketing pass (radix_sort.cu)
         const bool bucketed = sa != nullptr && n > (12u << 20);
-        LAUNCH(ctx, bwt_rerank_kernel, grid_for(rr_tiles, 1, 148 * 6), RR_BLOCK, 0, keys, sa, n, rr_tiles,
+        LAUNCH(ctx, bwt_rerank_kernel, grid_for(rr_tiles, 1, 148 * 6), RR_BLOCK, 0, keys, sa, n, rr_tiles, 0u,
                bucketed ? (u32 *)nullptr : d_rank, d_rs, d_hist4, d_counters, d_status, d_ticket);
         if (bucketed) RET(dev_scatter_perm(ctx, sa, d_rs, n, d_rank, (u32 *)keys, (u32 *)keys + n));
         CU(ctx, cudaMemcpyAsync(h_cnt, d_counters, 2 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
@@ -533,5 +547,52 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
     *primary = *h_primary;
     ctx->stats.bwt_rounds = rounds;
     ctx->stats.bwt_sort_passes = passes_total;
+    return BZAP_OK;
+}
+
+// ---- device-level building blocks for the distributed single-block path (include/bzap.h) ----------------
+int dev_init_keys(bzap_ctx *ctx, const u8 *d_text, u32 n, u32 lo, u32 m, u64 *d_keys)
+{
+    LAUNCH(ctx, bwt_init_keys_kernel, grid_for((m + IK_TILE - 1) / IK_TILE, 1, 148 * 8), IK_BLOCK, 0, d_text, n, lo, m, d_keys);
+    CU(ctx, cudaGetLastError());
+    return BZAP_OK;
+}
+
+// sparse ranks of an already sorted key run whose first element sits at global slot pos_base;
+// counts[0] = heads, counts[1] = singleton groups (both local: the caller patches the seams)
+int dev_rerank_run(bzap_ctx *ctx, const u64 *d_keys, u32 m, u32 pos_base, u32 *d_rs, u32 counts[2])
+{
+    const u32 rr_tiles = (m + RR_TILE - 1) / RR_TILE;
+    const size_t words = 4 * 256 + 8 + 2 * ((size_t)rr_tiles + 8);
+    u32 *d_ctl = arena_get<u32>(ctx, words);
+    if (!d_ctl) return bzap_fail(ctx, BZAP_ERR_NOMEM, "rerank scratch");
+    CU(ctx, cudaMemsetAsync(d_ctl, 0, words * sizeof(u32), ctx->stream));
+    u32 *d_hist4 = d_ctl, *d_counters = d_ctl + 4 * 256, *d_ticket = d_counters + 4;
+    u64 *d_status = (u64 *)(d_ctl + 4 * 256 + 8);
+    LAUNCH(ctx, bwt_rerank_kernel, grid_for(rr_tiles, 1, 148 * 6), RR_BLOCK, 0, d_keys, (const u32 *)nullptr, m, rr_tiles,
+           pos_base, (u32 *)nullptr, d_rs, d_hist4, d_counters, d_status, d_ticket);
+    u32 *h = (u32 *)(ctx->mailbox + 1024);
+    CU(ctx, cudaMemcpyAsync(h, d_counters, 2 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaGetLastError());
+    counts[0] = h[0];
+    counts[1] = h[1];
+    return BZAP_OK;
+}
+
+// last[j] = text[(sa[j] + n - 1) mod n] for the m suffix-array slots held by this GPU
+__global__ void __launch_bounds__(256)
+bwt_gather_slots_kernel(const u8 *__restrict__ text, const u32 *__restrict__ sa, u32 n, u32 m, u8 *__restrict__ last)
+{
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+        u32 s = sa[j];
+        last[j] = text[s == 0 ? n - 1 : s - 1];
+    }
+}
+int dev_gather_slots(bzap_ctx *ctx, const u8 *d_text, const u32 *d_sa, u32 n, u32 m, u8 *d_last)
+{
+    LAUNCH(ctx, bwt_gather_slots_kernel, grid_for(m, 256), 256, 0, d_text, d_sa, n, m, d_last);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaGetLastError());
     return BZAP_OK;
 }

@@ -48,21 +48,46 @@ __device__ __forceinline__ u32 ib_node_of(u32 row, u32 n, u32 nb, u32 primary)
 
 // node[j] = (next << 32) | len ; a regular splitter that coincides with `primary` is dropped
 // (next = NIL, len = 0): node nb covers that row.
+// Sub-list lengths are geometric, so one thread per sub-list would leave most lanes of a warp idle
+// while the longest one finishes.  Instead every lane keeps pulling sub-lists from a global work
+// counter (warp-aggregated, only when >= IB_REFILL lanes are idle): all lanes step until the list
+// of sub-lists is exhausted.
+#define IB_REFILL 8
 __global__ void __launch_bounds__(256)
-ibwt_walk_len_kernel(const u32 *__restrict__ T, u32 n, u32 nb, u32 primary, u64 *__restrict__ node)
+ibwt_walk_len_kernel(const u32 *__restrict__ T, u32 n, u32 nb, u32 primary, u64 *__restrict__ node, u32 *counter)
 {
-    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j > nb) return;
-    u32 row = j == nb ? primary : ib_splitter_row(j, n);
-    if (j < nb && row == primary) { node[j] = ((u64)IB_NIL << 32); return; }
-    u32 len = 0, nx;
-    do {
-        row = T[row];
-        ++len;
-        nx = ib_node_of(row, n, nb, primary);
-    } while (nx == IB_NIL);
-    // the list is cut open in front of `primary`: the node that reaches it becomes the tail
-    node[j] = ((u64)(nx == nb ? IB_NIL : nx) << 32) | len;
+    const u32 lane = lane_id();
+    u32 j = IB_NIL, row = 0, len = 0;
+    bool exhausted = false;
+    while (true) {
+        const u32 idle = __ballot_sync(FULL_MASK, j == IB_NIL);
+        if (idle == FULL_MASK && exhausted) break;
+        if (!exhausted && __popc(idle) >= IB_REFILL) {
+            const u32 want = (u32)__popc(idle);
+            u32 base = 0;
+            if (lane == 0) base = atomicAdd(counter, want);
+            base = __shfl_sync(FULL_MASK, base, 0);
+            if (j == IB_NIL) {
+                u32 mine = base + (u32)__popc(idle & lanemask_lt());
+                if (mine <= nb) {
+                    row = mine == nb ? primary : ib_splitter_row(mine, n);
+                    if (mine < nb && row == primary) node[mine] = ((u64)IB_NIL << 32);
+                    else { j = mine; len = 0; }
+                }
+            }
+            exhausted = base + want > nb;
+        }
+        if (j != IB_NIL) {
+            row = T[row];
+            ++len;
+            u32 nx = ib_node_of(row, n, nb, primary);
+            if (nx != IB_NIL) {
+                // the list is cut open in front of `primary`: the node that reaches it becomes the tail
+                node[j] = ((u64)(nx == nb ? IB_NIL : nx) << 32) | len;
+                j = IB_NIL;
+            }
+        }
+    }
 }
 
 // one pointer-jumping round: dist[j] += dist[next[j]]; next[j] = next[next[j]]
@@ -79,39 +104,81 @@ __global__ void __launch_bounds__(256) ibwt_wyllie_kernel(const u64 *__restrict_
     out[j] = a;
 }
 
-// F(r): byte c with cum[c] <= r < cum[c+1]
-__device__ __forceinline__ u32 ib_first_col(const u32 *s_cum, u32 r)
+// F(r): byte c with cum[c] <= r < cum[c+1].  A 4096-entry coarse table gives the first candidate
+// byte of r's slice; a short forward scan finishes (cum is monotone, 256 steps over N rows).
+#define IB_COARSE_LOG 12
+struct FirstCol {
+    u32 cum[257];
+    u8 coarse[1u << IB_COARSE_LOG];
+    u32 shift;
+};
+__device__ __forceinline__ void ib_first_col_init(FirstCol &F, const u32 *__restrict__ cum, u32 n)
 {
-    u32 lo = 0, hi = 256;                 // invariant: cum[lo] <= r < cum[hi]
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        u32 mid = (lo + hi) >> 1;
-        if (s_cum[mid] <= r) lo = mid; else hi = mid;
+    for (u32 i = threadIdx.x; i < 257; i += blockDim.x) F.cum[i] = cum[i];
+    u32 bits = 0;
+    while (((u64)1 << bits) < n) ++bits;
+    const u32 shift = bits > IB_COARSE_LOG ? bits - IB_COARSE_LOG : 0;
+    if (threadIdx.x == 0) F.shift = shift;
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < (1u << IB_COARSE_LOG); i += blockDim.x) {
+        u64 r = (u64)i << shift;                       // first row of the slice
+        u32 lo = 0, hi = 256;                          // largest c with cum[c] <= r (cum[0] = 0)
+        if (r >= n) lo = 255;
+        else
+            while (hi - lo > 1) {
+                u32 mid = (lo + hi) >> 1;
+                if (F.cum[mid] <= r) lo = mid; else hi = mid;
+            }
+        F.coarse[i] = (u8)lo;
     }
-    return lo;
+    __syncthreads();
+}
+__device__ __forceinline__ u32 ib_first_col(const FirstCol &F, u32 r)
+{
+    u32 c = F.coarse[r >> F.shift];
+    while (F.cum[c + 1] <= r) ++c;
+    return c;
 }
 
 // dist[j] (from the ranking) = bytes from splitter j to the end of the opened list; the list holds
-// cycle_len = dist[nb] bytes, so splitter j starts writing at cycle_len - dist[j].
+// cycle_len = dist[nb] bytes, so splitter j starts writing at cycle_len - dist[j].  Same lane
+// refill scheme as ibwt_walk_len_kernel.
 __global__ void __launch_bounds__(256)
 ibwt_walk_write_kernel(const u32 *__restrict__ T, u32 n, u32 nb, u32 primary, const u64 *__restrict__ len_node,
-                       const u64 *__restrict__ ranked, const u32 *__restrict__ cum, u8 *__restrict__ out)
+                       const u64 *__restrict__ ranked, const u32 *__restrict__ cum, u8 *__restrict__ out, u32 *counter)
 {
-    __shared__ u32 s_cum[257];
-    for (u32 i = threadIdx.x; i < 257; i += blockDim.x) s_cum[i] = cum[i];
-    __syncthreads();
-    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j > nb) return;
-    const u64 rk = ranked[j];
-    if ((u32)(rk >> 32) != IB_NIL) return;              // never reaches `primary`: another cycle
-    const u32 len = (u32)len_node[j];
-    if (len == 0) return;                               // dropped duplicate of `primary`
+    __shared__ FirstCol F;
+    ib_first_col_init(F, cum, n);
+    const u32 lane = lane_id();
     const u32 cycle_len = (u32)ranked[nb];
-    u32 o = cycle_len - (u32)rk;
-    u32 row = j == nb ? primary : ib_splitter_row(j, n);
-    for (u32 t = 0; t < len; ++t) {
-        out[o + t] = (u8)ib_first_col(s_cum, row);      // out[i] = L[T[x_i]] = F(x_i)   (main.cpp:71)
-        row = T[row];
+    u32 row = 0, o = 0, left = 0;
+    bool exhausted = false;
+    while (true) {
+        const u32 idle = __ballot_sync(FULL_MASK, left == 0);
+        if (idle == FULL_MASK && exhausted) break;
+        if (!exhausted && __popc(idle) >= IB_REFILL) {
+            const u32 want = (u32)__popc(idle);
+            u32 base = 0;
+            if (lane == 0) base = atomicAdd(counter, want);
+            base = __shfl_sync(FULL_MASK, base, 0);
+            if (left == 0) {
+                u32 mine = base + (u32)__popc(idle & lanemask_lt());
+                if (mine <= nb) {
+                    const u64 rk = ranked[mine];
+                    if ((u32)(rk >> 32) == IB_NIL) {          // reaches `primary`: on its cycle
+                        left = (u32)len_node[mine];           // 0 for the dropped duplicate of `primary`
+                        o = cycle_len - (u32)rk;
+                        row = mine == nb ? primary : ib_splitter_row(mine, n);
+                    }
+                }
+            }
+            exhausted = base + want > nb;
+        }
+        if (left) {
+            out[o++] = (u8)ib_first_col(F, row);              // out[i] = L[T[x_i]] = F(x_i)   (main.cpp:71)
+            row = T[row];
+            --left;
+        }
     }
 }
 
@@ -134,10 +201,13 @@ int dev_ibwt(bzap_ctx *ctx, const u8 *d_last, size_t n64, u64 primary64, u8 *d_o
     u32 *d_cum = arena_get<u32>(ctx, 260);
     u64 *d_len = arena_get<u64>(ctx, nodes);
     u64 *d_rank[2] = {arena_get<u64>(ctx, nodes), arena_get<u64>(ctx, nodes)};
-    if (!d_T || !d_cum || !d_len || !d_rank[0] || !d_rank[1]) return bzap_fail(ctx, BZAP_ERR_NOMEM, "ibwt scratch");
+    u32 *d_work = arena_get<u32>(ctx, 8);
+    if (!d_T || !d_cum || !d_len || !d_rank[0] || !d_rank[1] || !d_work) return bzap_fail(ctx, BZAP_ERR_NOMEM, "ibwt scratch");
+    CU(ctx, cudaMemsetAsync(d_work, 0, 8 * sizeof(u32), ctx->stream));
+    const u32 wgrid = nodes / 256 + 1 < 148u * 8u ? nodes / 256 + 1 : 148u * 8u;
     RET(dev_sort_positions_by_byte(ctx, d_last, n, d_T, d_cum));
     const u32 nblk = (nodes + 255) / 256;
-    LAUNCH(ctx, ibwt_walk_len_kernel, nblk, 256, 0, d_T, n, nb, primary, d_len);
+    LAUNCH(ctx, ibwt_walk_len_kernel, wgrid, 256, 0, d_T, n, nb, primary, d_len, d_work);
     // pointer jumping: after r rounds every node has jumped 2^r links
     int cur = 0;
     const u64 *src = d_len;
@@ -150,7 +220,7 @@ int dev_ibwt(bzap_ctx *ctx, const u8 *d_last, size_t n64, u64 primary64, u8 *d_o
         CU(ctx, cudaMemcpyAsync(d_rank[0], d_len, nodes * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
         src = d_rank[0];
     }
-    LAUNCH(ctx, ibwt_walk_write_kernel, nblk, 256, 0, d_T, n, nb, primary, d_len, src, d_cum, d_out);
+    LAUNCH(ctx, ibwt_walk_write_kernel, wgrid, 256, 0, d_T, n, nb, primary, d_len, src, d_cum, d_out, d_work + 1);
     u64 *h_cycle = (u64 *)(ctx->mailbox + 1056);
     CU(ctx, cudaMemcpyAsync(h_cycle, src + nb, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));

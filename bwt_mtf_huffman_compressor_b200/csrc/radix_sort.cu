@@ -15,6 +15,18 @@
 #include "device_common.cuh"
 
 #define RS_BLOCK 256
+#ifndef RS_MINBLOCKS
+#define RS_MINBLOCKS 3
+#endif
+#ifndef RS_EARLY_VALS
+#define RS_EARLY_VALS 0
+#endif
+#ifndef RS_LATE_LOOKBACK
+#define RS_LATE_LOOKBACK 1
+#endif
+#ifndef RS_LB_WIDE
+#define RS_LB_WIDE 4
+#endif
 #define RS_WARPS (RS_BLOCK / 32)
 #define RS_FLAG_AGG (1u << 30)
 #define RS_FLAG_INCL (2u << 30)
@@ -36,7 +48,7 @@ template <typename KeyT> __device__ __forceinline__ u32 digit_of(KeyT k, int shi
 
 // offsets = exclusive global digit offsets of this pass (256); status = tiles*256 zeroed words
 template <typename KeyT, int ITEMS, bool IOTA_VALS, bool WRITE_KEYS>
-__global__ void __launch_bounds__(RS_BLOCK, 3)
+__global__ void __launch_bounds__(RS_BLOCK, RS_MINBLOCKS)
 onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out, const u32 *__restrict__ vals_in,
                      u32 *__restrict__ vals_out, u32 n, int shift, const u32 *__restrict__ offsets, u32 *status,
                      u32 *ticket)
@@ -78,49 +90,62 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
     }
     __syncthreads();
 
-    // thread b owns digit b: prefix over warps, publish, scan over digits, look back
+    // thread b owns digit b: prefix over warps, publish the tile's count, scan over digits
+    const u32 bin = tid;
+    u32 *my_status = status + (size_t)tile * 256 + bin;
+    u32 count, tile_start;
     {
-        const u32 b = tid;
         u32 run = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) {
-            u32 t = S.whist[w][b];
-            S.whist[w][b] = run;
+            u32 t = S.whist[w][bin];
+            S.whist[w][bin] = run;
             run += t;
         }
-        const u32 count = run;
-        u32 *my_status = status + (size_t)tile * 256 + b;
+        count = run;
         if (tile == 0) st_relaxed(my_status, RS_FLAG_INCL | count);
         else st_relaxed(my_status, RS_FLAG_AGG | count);
         u32 total;
-        u32 tile_start = block_exclusive_sum(count, S.scan_tmp, &total);
+        tile_start = block_exclusive_sum(count, S.scan_tmp, &total);
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) S.whist[w][bin] += tile_start;
+    }
+    // global base of digit `bin`: decoupled look-back over the previous tiles.  It only feeds the
+    // final write-out, so (RS_LATE_LOOKBACK) it runs after the shared-memory regroup, which gives
+    // the predecessors time to publish their inclusive prefixes; status words are fetched
+    // RS_LB_WIDE at a time so that a deep walk is not a chain of dependent L2 round trips.
+    auto look_back = [&]() {
         u32 excl = 0;
         if (tile > 0) {
             int t = (int)tile - 1;
-            while (true) {
-                const u32 *p = status + (size_t)t * 256 + b;
-                u32 s;
-                do { s = ld_relaxed(p); } while ((s >> 30) == 0);
-                excl += s & RS_VALUE_MASK;
-                if ((s >> 30) == 2) break;
-                --t;
+            bool done = false;
+            while (!done) {
+                u32 sv[RS_LB_WIDE];
+#pragma unroll
+                for (int q = 0; q < RS_LB_WIDE; ++q)
+                    sv[q] = t - q >= 0 ? ld_relaxed(status + (size_t)(t - q) * 256 + bin) : RS_FLAG_INCL;
+#pragma unroll
+                for (int q = 0; q < RS_LB_WIDE; ++q) {
+                    if (!done) {
+                        u32 v = sv[q];
+                        while ((v >> 30) == 0) v = ld_relaxed(status + (size_t)(t - q) * 256 + bin);
+                        excl += v & RS_VALUE_MASK;
+                        done = (v >> 30) == 2;
+                    }
+                }
+                t -= RS_LB_WIDE;
             }
             st_relaxed(my_status, RS_FLAG_INCL | (excl + count));
         }
-        S.adj[b] = offsets[b] + excl - tile_start;
-#pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) S.whist[w][b] += tile_start;
-    }
+        S.adj[bin] = offsets[bin] + excl - tile_start;
+    };
+#if !RS_LATE_LOOKBACK
+    look_back();
+#endif
     __syncthreads();
 
-    // regroup keys by digit in shared memory; rnk[] becomes the position inside the sorted tile
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-        u32 pos = wh[digit_of(key[j], shift)] + rnk[j];
-        S.keys[pos] = key[j];
-        rnk[j] = pos;
-    }
-    // payload loads are issued only now (the key registers are dead) and fly during the key write-out
+    // regroup keys and payloads by digit in shared memory
+#if RS_EARLY_VALS
     u32 val[ITEMS];
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
@@ -128,26 +153,40 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
         if (IOTA_VALS) val[j] = idx;
         else val[j] = idx < n ? vals_in[idx] : 0u;
     }
+#endif
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        u32 pos = wh[digit_of(key[j], shift)] + rnk[j];
+        S.keys[pos] = key[j];
+        rnk[j] = pos;
+    }
+#if !RS_EARLY_VALS
+    // payload loads are issued only now: the key registers are dead
+    u32 val[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        u32 idx = wbase + j * 32u + lane;
+        if (IOTA_VALS) val[j] = idx;
+        else val[j] = idx < n ? vals_in[idx] : 0u;
+    }
+#endif
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) S.vals[rnk[j]] = val[j];
+#if RS_LATE_LOOKBACK
+    look_back();
+#endif
     __syncthreads();
 
     // contiguous per-digit runs go out; padding keys (digit 255, highest tile index) sit last
-    if (WRITE_KEYS) {
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            u32 idx = tid + i * RS_BLOCK;
-            if (idx < valid) {
-                KeyT k = S.keys[idx];
-                keys_out[S.adj[digit_of(k, shift)] + idx] = k;
-            }
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) S.vals[rnk[j]] = val[j];
-    __syncthreads();
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         u32 idx = tid + i * RS_BLOCK;
-        if (idx < valid) vals_out[S.adj[digit_of(S.keys[idx], shift)] + idx] = S.vals[idx];
+        if (idx < valid) {
+            KeyT k = S.keys[idx];
+            u32 g = S.adj[digit_of(k, shift)] + idx;
+            if (WRITE_KEYS) keys_out[g] = k;
+            vals_out[g] = S.vals[idx];
+        }
     }
 }
 
@@ -205,8 +244,13 @@ __global__ void radix_cum_u8_kernel(const u32 *__restrict__ hist, u32 *__restric
 }
 
 // ---- host drivers ------------------------------------------------------------------------------
+#ifndef RS_ITEMS_64
 #define RS_ITEMS_64 16
+#endif
 #define RS_ITEMS_8 16
+#ifndef RS_ITEMS_32
+#define RS_ITEMS_32 20
+#endif
 
 size_t sort_scratch_bytes(u32 n)
 {
@@ -342,7 +386,7 @@ int dev_scatter_perm(bzap_ctx *ctx, const u32 *d_perm, const u32 *d_vals, u32 n,
         LAUNCH(ctx, scatter_u32_kernel, sgrid, 256, 0, d_perm, d_vals, n, d_out);
         return BZAP_OK;
     }
-    constexpr int ITEMS = 16;
+    constexpr int ITEMS = RS_ITEMS_32;
     const u32 tiles = (n + RS_BLOCK * ITEMS - 1) / (RS_BLOCK * ITEMS);
     const size_t status_words = (size_t)tiles * 256;
     u32 *d_ctl = arena_get<u32>(ctx, 256 + 8 + status_words);
@@ -358,6 +402,116 @@ int dev_scatter_perm(bzap_ctx *ctx, const u32 *d_perm, const u32 *d_vals, u32 n,
     RET(set_smem_attr(ctx, k, smem));
     LAUNCH(ctx, k, tiles, RS_BLOCK, smem, d_perm, d_tmp_idx, d_vals, d_tmp_vals, n, shift, d_offsets, d_status, d_ticket);
     LAUNCH(ctx, scatter_u32_kernel, sgrid, 256, 0, d_tmp_idx, d_tmp_vals, n, d_out);
+    CU(ctx, cudaGetLastError());
+    return BZAP_OK;
+}
+
+// ---- generic 64-bit pair sort with its own digit histograms (distributed path, device pointers) -----------
+__global__ void __launch_bounds__(256) radix_hist_u64_kernel(const u64 *__restrict__ keys, u32 n, u32 *hist8)
+{
+    __shared__ u32 s_h[8 * 256];
+    for (u32 i = threadIdx.x; i < 8 * 256; i += 256) s_h[i] = 0;
+    __syncthreads();
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        u64 k = keys[i];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) atomicAdd(&s_h[p * 256 + ((u32)(k >> (8 * p)) & 0xffu)], 1u);
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < 8 * 256; i += 256) {
+        u32 c = s_h[i];
+        if (c) atomicAdd(&hist8[i], c);
+    }
+}
+
+int dev_sort_pairs_generic(bzap_ctx *ctx, u64 *d_keys, u32 *d_vals, u32 m, u64 *d_keys_tmp, u32 *d_vals_tmp,
+                           int *result_in_tmp)
+{
+    u32 *d_hist8 = arena_get<u32>(ctx, 8 * 256);
+    if (!d_hist8) return bzap_fail(ctx, BZAP_ERR_NOMEM, "sort scratch");
+    CU(ctx, cudaMemsetAsync(d_hist8, 0, 8 * 256 * sizeof(u32), ctx->stream));
+    LAUNCH(ctx, radix_hist_u64_kernel, min((m + 255) / 256, 148u * 8u), 256, 0, d_keys, m, d_hist8);
+    SortBuffers sb;
+    sb.keys[0] = d_keys; sb.keys[1] = d_keys_tmp;
+    sb.vals[0] = d_vals; sb.vals[1] = d_vals_tmp;
+    u64 *ok = nullptr;
+    u32 *ov = nullptr;
+    int passes = 0;
+    RET(dev_sort_pairs64(ctx, &sb, m, 64, d_hist8, false, &ok, &ov, &passes));
+    *result_in_tmp = ok == d_keys_tmp;
+    return BZAP_OK;
+}
+
+// dest[i] = number of splitters (K, I) with (K, I) <= (key[i], val[i]) lexicographically
+__global__ void __launch_bounds__(256)
+partition_dest_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ vals, u32 m, const u64 *__restrict__ sk,
+                      const u32 *__restrict__ sv, int ns, u8 *__restrict__ dest)
+{
+    __shared__ u64 s_k[256];
+    __shared__ u32 s_v[256];
+    if ((int)threadIdx.x < ns) { s_k[threadIdx.x] = sk[threadIdx.x]; s_v[threadIdx.x] = sv[threadIdx.x]; }
+    __syncthreads();
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        u64 k = keys[i];
+        u32 v = vals[i];
+        int lo = 0, hi = ns;                       // first splitter greater than (k, v)
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            bool le = s_k[mid] < k || (s_k[mid] == k && s_v[mid] <= v);
+            if (le) lo = mid + 1; else hi = mid;
+        }
+        dest[i] = (u8)lo;
+    }
+}
+
+int dev_partition_dest(bzap_ctx *ctx, const u64 *d_keys, const u32 *d_vals, u32 m, const u64 *h_sk, const u32 *h_sv, int ns,
+                       u8 *d_dest)
+{
+    if (ns < 0 || ns > 255) return bzap_fail(ctx, BZAP_ERR_ARG, "splitters");
+    u64 *d_sk = arena_get<u64>(ctx, 256);
+    u32 *d_sv = arena_get<u32>(ctx, 256);
+    if (!d_sk || !d_sv) return bzap_fail(ctx, BZAP_ERR_NOMEM, "partition scratch");
+    u64 *m_sk = (u64 *)(ctx->mailbox + 20480);
+    u32 *m_sv = (u32 *)(ctx->mailbox + 20480 + 2048);
+    for (int i = 0; i < ns; ++i) { m_sk[i] = h_sk[i]; m_sv[i] = h_sv[i]; }
+    if (ns) {
+        CU(ctx, cudaMemcpyAsync(d_sk, m_sk, ns * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(d_sv, m_sv, ns * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    LAUNCH(ctx, partition_dest_kernel, min((m + 255) / 256, 148u * 16u), 256, 0, d_keys, d_vals, m, d_sk, d_sv, ns, d_dest);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaGetLastError());
+    return BZAP_OK;
+}
+
+// out_k[j] = keys[perm[j]], out_v[j] = vals[perm[j]]  (regrouping by destination before an all-to-all)
+__global__ void __launch_bounds__(256)
+permute_pairs_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ vals, const u32 *__restrict__ perm, u32 m,
+                     u64 *__restrict__ out_k, u32 *__restrict__ out_v)
+{
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+        u32 p = perm[j];
+        if (keys) out_k[j] = keys[p];
+        out_v[j] = vals[p];
+    }
+}
+int dev_permute_pairs(bzap_ctx *ctx, const u64 *d_keys, const u32 *d_vals, const u32 *d_perm, u32 m, u64 *d_out_k, u32 *d_out_v)
+{
+    LAUNCH(ctx, permute_pairs_kernel, min((m + 255) / 256, 148u * 16u), 256, 0, d_keys, d_vals, d_perm, m, d_out_k, d_out_v);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaGetLastError());
+    return BZAP_OK;
+}
+// out[idx[j] - idx_offset] = vals[j]
+__global__ void __launch_bounds__(256)
+scatter_offset_kernel(const u32 *__restrict__ idx, const u32 *__restrict__ vals, u32 m, u32 off, u32 *__restrict__ out)
+{
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) out[idx[j] - off] = vals[j];
+}
+int dev_scatter_offset(bzap_ctx *ctx, const u32 *d_idx, const u32 *d_vals, u32 m, u32 off, u32 *d_out)
+{
+    LAUNCH(ctx, scatter_offset_kernel, min((m + 255) / 256, 148u * 16u), 256, 0, d_idx, d_vals, m, off, d_out);
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaGetLastError());
     return BZAP_OK;
 }

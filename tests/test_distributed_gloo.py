@@ -1,0 +1,135 @@
+"""Host logic of the distributed single-block BWT (bwt_mtf_huffman_compressor_b200/distributed.py)
+on CPU: world_size 2 and 3 gloo processes, the per-GPU steps replaced by a numpy stand-in that
+lives HERE (test infrastructure; the product only has GpuBackend).  Checks plans, splitters under
+massive key duplication, seam fix-up and termination against the oracle BWT."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from bwt_mtf_huffman_compressor_b200 import distributed as D  # noqa: E402
+
+
+class NumpyBackend:
+    def init_keys(self, text, n, lo, m):
+        t = text.numpy()
+        i = (np.arange(lo, lo + m)[:, None] + np.arange(8)[None, :]) % n
+        b = t[i].astype(np.uint64)
+        k = np.zeros(m, dtype=np.uint64)
+        for j in range(8):
+            k = (k << np.uint64(8)) | b[:, j]
+        return torch.from_numpy(k.view(np.int64).copy())
+
+    def sort_pairs(self, keys, vals):
+        k = keys.numpy().view(np.uint64)
+        o = np.argsort(k, kind="stable")
+        return torch.from_numpy(k[o].view(np.int64).copy()), torch.from_numpy(vals.numpy()[o].copy())
+
+    def rerank(self, keys_sorted, pos_base):
+        k = keys_sorted.numpy()
+        m = k.size
+        if m == 0:
+            return torch.zeros(0, dtype=torch.int32), 0
+        head = np.ones(m, dtype=bool)
+        head[1:] = k[1:] != k[:-1]
+        rs = pos_base + np.maximum.accumulate(np.where(head, np.arange(m), 0))
+        return torch.from_numpy(rs.astype(np.int32)), int(head.sum())
+
+    def partition_dest(self, keys, vals, sk, sv):
+        k = keys.numpy().view(np.uint64)
+        v = vals.numpy().astype(np.uint32)
+        d = np.zeros(k.size, dtype=np.uint8)
+        for a, b in zip(sk, sv):
+            d += ((k > a) | ((k == a) & (v >= b))).astype(np.uint8)
+        return torch.from_numpy(d)
+
+    def permute_pairs(self, keys, vals, perm):
+        p = perm.long()
+        return (None if keys is None else keys[p]), vals[p]
+
+    def scatter(self, idx, vals, offset, out):
+        out[(idx - offset).long()] = vals
+
+    def gather_last(self, text, n, sa):
+        return text[(sa.long() + (n - 1)) % n]
+
+    def stable_perm_by_byte(self, dest):
+        d = dest.numpy()
+        perm = np.argsort(d, kind="stable").astype(np.int32)
+        cum = np.concatenate([[0], np.cumsum(np.bincount(d, minlength=256))]).astype(np.int64)
+        return torch.from_numpy(perm), cum
+
+
+def test_shift_plan_covers_every_range_exactly_once():
+    for n, world, k in [(10, 2, 8), (1000, 3, 16), (1000, 3, 999), (7, 4, 8), (64, 8, 64), (100, 8, 3)]:
+        shard, b = D.shard_bounds(n, world)
+        plan = D.shift_plan(n, world, k % n)
+        for d in range(world):
+            m = b[d + 1] - b[d]
+            got = []
+            for s in range(world):
+                for a, ln in plan[s][d]:
+                    assert b[s] <= a and a + ln <= b[s + 1]
+                    got.extend(range(a, a + ln))
+            want = sorted((b[d] + i + k) % n for i in range(m))
+            assert sorted(got) == want
+
+
+def _cases():
+    rng = np.random.default_rng(3)
+    return {
+        "random": rng.integers(0, 256, 5000, dtype=np.uint8),
+        "binary": rng.integers(0, 2, 4097, dtype=np.uint8),
+        "all_a": np.full(3001, 97, dtype=np.uint8),                 # every key equal: index-balanced splitters
+        "abab": np.resize(np.frombuffer(b"ab", dtype=np.uint8), 2048),
+        "abc_trunc": np.resize(np.frombuffer(b"abc", dtype=np.uint8), 1000),
+        "a_then_b": np.concatenate([np.full(1500, 97, dtype=np.uint8), [98]]).astype(np.uint8),
+        "tiny": np.frombuffer(b"banana", dtype=np.uint8).copy(),
+        "text": np.frombuffer((b"the quick brown fox jumps over the lazy dog " * 60), dtype=np.uint8).copy(),
+    }
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out = {}
+    for name, d in _cases().items():
+        last, primary, rounds = D.distributed_bwt(torch.from_numpy(d.copy()), None, NumpyBackend())
+        out[name] = (None if last is None else last.numpy().tobytes(), primary, rounds)
+    dist.barrier()
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_bwt_matches_oracle_over_gloo(world):
+    import oracle_lib as O
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for name, d in _cases().items():
+        ol, op = O.o_bwt(d)
+        last, primary, rounds = res[0][name]
+        assert primary == op, name
+        assert last == ol.tobytes(), name
+        for r in range(1, world):
+            assert res[r][name][0] is None and res[r][name][1] == op
