@@ -202,7 +202,7 @@ def run_ours(args):
     if not np.array_equal(h_back.numpy(), data):
         raise SystemExit("bench.py: host round trip is not bit exact")
 
-    cal = calgary_batch(bz, W, rank, world, dist)
+    cal = None if args.no_calgary else calgary_batch(bz, W, rank, world, dist)
 
     t = torch.tensor([dev_ms, host_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -390,6 +390,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=N_TEXT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-calgary", action="store_true", help="skip the Calgary batch (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

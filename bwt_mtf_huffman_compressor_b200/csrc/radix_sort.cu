@@ -27,6 +27,9 @@
 #ifndef RS_LB_WIDE
 #define RS_LB_WIDE 4
 #endif
+#ifndef RS_BROADCAST_RANK
+#define RS_BROADCAST_RANK 0
+#endif
 #define RS_WARPS (RS_BLOCK / 32)
 #define RS_FLAG_AGG (1u << 30)
 #define RS_FLAG_INCL (2u << 30)
@@ -64,10 +67,16 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
 
     KeyT key[ITEMS];
     u32 rnk[ITEMS];
+    const bool full_tile = valid == TILE;          // uniform: all but the last tile skip the bounds checks
+    if (full_tile) {
 #pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-        u32 idx = wbase + j * 32u + lane;
-        key[j] = idx < n ? keys_in[idx] : (KeyT)~(KeyT)0;
+        for (int j = 0; j < ITEMS; ++j) key[j] = keys_in[wbase + j * 32u + lane];
+    } else {
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            u32 idx = wbase + j * 32u + lane;
+            key[j] = idx < n ? keys_in[idx] : (KeyT)~(KeyT)0;
+        }
     }
     for (u32 i = lane; i < 256; i += 32) S.whist[warp][i] = 0;
     __syncwarp();
@@ -78,6 +87,16 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
     for (int j = 0; j < ITEMS; ++j) {
         u32 d = digit_of(key[j], shift);
         u32 m = __match_any_sync(FULL_MASK, d);
+#if RS_BROADCAST_RANK
+        // every lane of a digit group reads the group's counter (a broadcast), the lowest lane
+        // writes it back: no shuffle, no divergent region
+        u32 below = (u32)__popc(m & lanemask_lt());
+        u32 prev = wh[d];
+        __syncwarp();
+        if (below == 0) wh[d] = prev + (u32)__popc(m);
+        rnk[j] = prev + below;
+        __syncwarp();
+#else
         u32 leader = (u32)__ffs(m) - 1u;
         u32 prev = 0;
         if (lane == leader) {
@@ -87,6 +106,7 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
         prev = __shfl_sync(FULL_MASK, prev, leader);
         rnk[j] = prev + (u32)__popc(m & lanemask_lt());
         __syncwarp();
+#endif
     }
     __syncthreads();
 
@@ -151,7 +171,7 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
     for (int j = 0; j < ITEMS; ++j) {
         u32 idx = wbase + j * 32u + lane;
         if (IOTA_VALS) val[j] = idx;
-        else val[j] = idx < n ? vals_in[idx] : 0u;
+        else val[j] = (full_tile || idx < n) ? vals_in[idx] : 0u;
     }
 #endif
 #pragma unroll
@@ -167,7 +187,7 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
     for (int j = 0; j < ITEMS; ++j) {
         u32 idx = wbase + j * 32u + lane;
         if (IOTA_VALS) val[j] = idx;
-        else val[j] = idx < n ? vals_in[idx] : 0u;
+        else val[j] = (full_tile || idx < n) ? vals_in[idx] : 0u;
     }
 #endif
 #pragma unroll
@@ -181,7 +201,7 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
 #pragma unroll
     for (int i = 0; i < ITEMS; ++i) {
         u32 idx = tid + i * RS_BLOCK;
-        if (idx < valid) {
+        if (full_tile || idx < valid) {
             KeyT k = S.keys[idx];
             u32 g = S.adj[digit_of(k, shift)] + idx;
             if (WRITE_KEYS) keys_out[g] = k;
