@@ -27,6 +27,9 @@
 #ifndef RS_LB_WIDE
 #define RS_LB_WIDE 4
 #endif
+#ifndef RS_ASYNC_VALS
+#define RS_ASYNC_VALS 0
+#endif
 #ifndef RS_BROADCAST_RANK
 #define RS_BROADCAST_RANK 0
 #endif
@@ -42,6 +45,9 @@ template <typename KeyT, int ITEMS> struct RsSmem {
     u32 adj[256];
     u32 scan_tmp[40];
     u32 ticket;
+#if RS_ASYNC_VALS
+    u32 vstage[RS_BLOCK * ITEMS];      // payloads land here by cp.async while the keys are ranked
+#endif
 };
 
 template <typename KeyT> __device__ __forceinline__ u32 digit_of(KeyT k, int shift)
@@ -78,6 +84,21 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
             key[j] = idx < n ? keys_in[idx] : (KeyT)~(KeyT)0;
         }
     }
+#if RS_ASYNC_VALS
+    // payloads: asynchronous global->shared copies (LDGSTS), no registers held, consumed after the
+    // ranking, the digit scan and the key regroup
+    if (!IOTA_VALS) {
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            u32 idx = wbase + j * 32u + lane;
+            if (full_tile || idx < n) {
+                u32 dst = (u32)__cvta_generic_to_shared(&S.vstage[warp * (32u * ITEMS) + j * 32u + lane]);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(vals_in + idx) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+#endif
     for (u32 i = lane; i < 256; i += 32) S.whist[warp][i] = 0;
     __syncwarp();
 
@@ -180,7 +201,15 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
         S.keys[pos] = key[j];
         rnk[j] = pos;
     }
-#if !RS_EARLY_VALS
+#if RS_ASYNC_VALS
+    u32 val[ITEMS];
+    if (!IOTA_VALS) asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        if (IOTA_VALS) val[j] = wbase + j * 32u + lane;
+        else val[j] = S.vstage[warp * (32u * ITEMS) + j * 32u + lane];     // this thread's own copies
+    }
+#elif !RS_EARLY_VALS
     // payload loads are issued only now: the key registers are dead
     u32 val[ITEMS];
 #pragma unroll
