@@ -82,9 +82,12 @@ __global__ void __launch_bounds__(256) bwt_pair_keys_kernel(const u32 *__restric
 // order), rs[j] = the same rank in sorted order, number of groups, number of singleton groups, and
 // the 4 x 256 histogram of rank digits for the next round's passes.  Persistent blocks take tiles
 // by ticket so that the shared-memory histogram is flushed once per block, not once per tile.
+// blocked accesses (thread t owns elements 8t..8t+7) would put 16 lanes on one bank pair: one pad
+// slot per 8 elements makes the lane stride 9 (conflict free for 32- and 64-bit words)
+#define RR_PAD(x) ((x) + ((x) >> 3))
 struct RrSmem {
-    u64 keys[RR_TILE + 2];
-    u32 r[RR_TILE];
+    u64 keys[RR_PAD(RR_TILE + 2) + 1];
+    u32 r[RR_PAD(RR_TILE) + 1];
     u32 hist[4][256];
     u32 tmp[40];
     u32 ticket;
@@ -122,8 +125,8 @@ bwt_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, u32 
     while (tile < ntiles) {
         const u32 base = tile * RR_TILE;
 #pragma unroll
-        for (int i = 0; i < RR_ITEMS; ++i) S.keys[tid + i * RR_BLOCK + 1] = kreg[i];
-        if (tid == 0) { S.keys[0] = kprev; S.keys[RR_TILE + 1] = knext; }
+        for (int i = 0; i < RR_ITEMS; ++i) S.keys[RR_PAD(tid + i * RR_BLOCK + 1)] = kreg[i];
+        if (tid == 0) { S.keys[0] = kprev; S.keys[RR_PAD(RR_TILE + 1)] = knext; }
         const u32 next_tile = take_ticket(ticket, &S.ticket);     // (barriers inside publish S.keys)
         fetch(next_tile);
 
@@ -134,8 +137,9 @@ bwt_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, u32 
         for (int i = 0; i < RR_ITEMS; ++i) {
             u32 o = tid * RR_ITEMS + i;
             u32 p = base + o;
-            bool head = p < n && (p == 0 || S.keys[o + 1] != S.keys[o]);
-            bool next_head = p + 1 >= n || S.keys[o + 2] != S.keys[o + 1];
+            const u64 k0 = S.keys[RR_PAD(o)], k1 = S.keys[RR_PAD(o + 1)], k2 = S.keys[RR_PAD(o + 2)];
+            bool head = p < n && (p == 0 || k1 != k0);
+            bool next_head = p + 1 >= n || k2 != k1;
             if (head) { cur = pos_base + p; ++nheads; nsingle += next_head; }
             loc[i] = cur;
         }
@@ -158,7 +162,7 @@ bwt_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, u32 
             u32 o = tid * RR_ITEMS + i;
             if (base + o < n) {
                 u32 r = max(pre, loc[i]);
-                S.r[o] = r;
+                S.r[RR_PAD(o)] = r;
 #pragma unroll
                 for (int d = 0; d < 4; ++d) {
                     u32 dig = (r >> (8 * d)) & 0xff;
@@ -181,7 +185,7 @@ bwt_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, u32 
             u32 o = tid + i * RR_BLOCK;
             u32 p = base + o;
             if (p < n) {
-                u32 r = S.r[o];
+                u32 r = S.r[RR_PAD(o)];
                 rs[p] = r;
                 if (rank) rank[sa ? sa[p] : p] = r;          // nullptr: a bucketed scatter follows
             }
@@ -222,6 +226,8 @@ __device__ __forceinline__ u32 compact_offset(u32 cnt, u32 tile, u64 *status, u3
 
 // after the last full round: sorted position j is settled iff its group is a singleton, i.e.
 // rs[j] == j and rs[j+1] == j+1.  Survivors keep their order: (start, group rank r1).
+#define CL_ITEMS 16
+#define CL_TILE (AC_BLOCK * CL_ITEMS)
 __global__ void __launch_bounds__(AC_BLOCK)
 bwt_collect_active_kernel(const u32 *__restrict__ rs, const u32 *__restrict__ sa, u32 n, u32 *__restrict__ act_idx,
                           u32 *__restrict__ act_r1, u64 *status, u32 *ticket)
@@ -229,22 +235,22 @@ bwt_collect_active_kernel(const u32 *__restrict__ rs, const u32 *__restrict__ sa
     __shared__ u32 s_tmp[40];
     __shared__ u32 s_ticket, s_base;
     const u32 tile = take_ticket(ticket, &s_ticket);
-    const u32 j0 = tile * AC_TILE + threadIdx.x * AC_ITEMS;
-    u32 r[AC_ITEMS + 1];
+    const u32 j0 = tile * CL_TILE + threadIdx.x * CL_ITEMS;
+    u32 r[CL_ITEMS + 1];
 #pragma unroll
-    for (int i = 0; i <= AC_ITEMS; ++i) r[i] = j0 + i < n ? rs[j0 + i] : j0 + i;   // past the end counts as a head
-    bool keep[AC_ITEMS];
-    u32 cnt = 0;
+    for (int i = 0; i <= CL_ITEMS; ++i) r[i] = j0 + i < n ? rs[j0 + i] : j0 + i;   // past the end counts as a head
+    u32 keep = 0, cnt = 0;
 #pragma unroll
-    for (int i = 0; i < AC_ITEMS; ++i) {
+    for (int i = 0; i < CL_ITEMS; ++i) {
         u32 j = j0 + i;
-        keep[i] = j < n && !(r[i] == j && r[i + 1] == j + 1);
-        cnt += keep[i];
+        bool k = j < n && !(r[i] == j && r[i + 1] == j + 1);
+        keep |= (u32)k << i;
+        cnt += k;
     }
     u32 o = compact_offset(cnt, tile, status, s_tmp, &s_base);
 #pragma unroll
-    for (int i = 0; i < AC_ITEMS; ++i)
-        if (keep[i]) {
+    for (int i = 0; i < CL_ITEMS; ++i)
+        if ((keep >> i) & 1u) {
             act_idx[o] = sa ? sa[j0 + i] : j0 + i;
             act_r1[o] = r[i];
             ++o;
@@ -437,8 +443,9 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
     u32 *d_hist8 = arena_get<u32>(ctx, 8 * 256);
     const size_t status_u64 = (size_t)(rr_tiles > 2 * ac_tiles_max ? rr_tiles : 2 * ac_tiles_max) + 8;
     u32 *d_rrctl = arena_get<u32>(ctx, 4 * 256 + 8 + 2 * status_u64);
-    const u32 ctiles = (n + AC_TILE - 1) / AC_TILE;
-    u64 *cstatus = arena_get<u64>(ctx, (size_t)ctiles + 4);
+    const u32 ctiles = (n + CL_TILE - 1) / CL_TILE;
+    // also serves the survivor compaction of the active rounds (<= n/2 elements in AC_TILE tiles)
+    u64 *cstatus = arena_get<u64>(ctx, (size_t)(ctiles > ac_tiles_max ? ctiles : ac_tiles_max) + 4);
     if (!sb.keys[0] || !sb.keys[1] || !sb.vals[0] || !sb.vals[1] || !d_rank || !d_rs || !d_hist8 || !d_rrctl || !cstatus)
         return bzap_fail(ctx, BZAP_ERR_NOMEM, "bwt scratch");
     u32 *d_hist4 = d_rrctl, *d_counters = d_rrctl + 4 * 256, *d_ticket = d_counters + 4;

@@ -138,8 +138,10 @@ __global__ void __launch_bounds__(256) mtf_scan_top_kernel(u32 *__restrict__ gro
     }
 }
 
-// one warp per chunk: key[s] = last occurrence before the chunk (or 255 - s if never seen, which
-// orders unseen symbols ascending after all seen ones); list position = number of larger keys
+// one warp per chunk.  key[s] = last occurrence of symbol s before the chunk (0 = never seen).
+// List = seen symbols by decreasing key, then the unseen ones in ascending symbol order.  Only the
+// seen symbols (a few dozen on text) need ranking: they are compacted first, each is ranked against
+// the compacted keys, and an unseen symbol's slot follows from ballots alone.
 __global__ void __launch_bounds__(256)
 mtf_lists_kernel(const u32 *__restrict__ last, const u32 *__restrict__ group_tot, u32 nchunks, u8 *__restrict__ lists)
 {
@@ -148,22 +150,28 @@ mtf_lists_kernel(const u32 *__restrict__ last, const u32 *__restrict__ group_tot
     const u32 c = blockIdx.x * 8 + warp;
     if (c >= nchunks) return;
     const u32 g = c / MTF_GROUP;
-    u32 key[8];
+    u32 key[8], seen_below[8];
+    u32 nseen = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        u32 s = lane + 32u * i;
+        u32 s = lane + 32u * i;                       // symbols in increasing order over (i, lane)
         u32 k = max(last[(size_t)c * 256 + s], group_tot[(size_t)g * 256 + s]);
-        if (k == 0) k = 255u - s;
         key[i] = k;
-        s_key[warp][s] = k;
+        u32 m = __ballot_sync(FULL_MASK, k != 0);
+        seen_below[i] = nseen + (u32)__popc(m & lanemask_lt());     // seen symbols smaller than s
+        if (k) s_key[warp][seen_below[i]] = k;
+        nseen += (u32)__popc(m);
     }
+    for (u32 t = nseen + lane; t < ((nseen + 3u) & ~3u); t += 32) s_key[warp][t] = 0;   // pad to a multiple of 4
     __syncwarp();
-    u32 pos[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (u32 t = 0; t < 256; t += 4) {
+    u32 pos[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) pos[i] = key[i] ? 0u : nseen + (lane + 32u * i) - seen_below[i];
+    for (u32 t = 0; t < nseen; t += 4) {
         uint4 o = *reinterpret_cast<const uint4 *>(&s_key[warp][t]);
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-            pos[i] += (o.x > key[i]) + (o.y > key[i]) + (o.z > key[i]) + (o.w > key[i]);
+            if (key[i]) pos[i] += (o.x > key[i]) + (o.y > key[i]) + (o.z > key[i]) + (o.w > key[i]);
     }
     u8 *out = lists + (size_t)c * 256;
 #pragma unroll
