@@ -95,20 +95,70 @@ struct RrSmem {
     u32 heads, singles;
 };
 
+// Work split: block b owns a CONTIGUOUS range of tiles and carries its running "last head" in
+// shared memory, so the only cross-block dependency is the last head before the range.  Every block
+// first finds the last head INSIDE its range by scanning backwards from the range end (the first
+// chunk almost always contains one) and publishes it at once -- publishing never waits on another
+// block, so there is no look-back chain -- then reads its predecessors' words until one holds a head.
+#define RR_NONE (1ull << 62)
+#define RR_FOUND (2ull << 62)
 __global__ void __launch_bounds__(RR_BLOCK)
 bwt_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, u32 n, u32 ntiles, u32 pos_base,
                   u32 *__restrict__ rank,
                   u32 *__restrict__ rs, u32 *hist4, u32 *counters /* [0]=groups [1]=singletons */, u64 *status,
-                  u32 *ticket)
+                  u32 *ticket /* unused */)
 {
     __shared__ RrSmem S;
     const u32 tid = threadIdx.x;
+    const u32 tpb = (ntiles + gridDim.x - 1) / gridDim.x;          // tiles per block
+    const u32 t0 = blockIdx.x * tpb, t1 = min(ntiles, t0 + tpb);
+    const u32 lo = t0 * RR_TILE, hi = min(n, t1 * RR_TILE);
     for (u32 i = tid; i < 4 * 256; i += RR_BLOCK) (&S.hist[0][0])[i] = 0;
-    if (tid == 0) { S.heads = 0; S.singles = 0; }
-    // software pipeline: the next tile's keys are in flight while the current tile is processed
+    if (tid == 0) { S.heads = 0; S.singles = 0; S.tile_prefix = 0; }
+    __syncthreads();
+    // 1. last head inside [lo, hi): block-wide backward scan, RR_TILE positions per step
+    if (t0 < t1) {
+        u32 found = 0;                                             // pos_base + position + 1, 0 = none
+        u32 end = hi;
+        while (end > lo && !found) {
+            const u32 beg = end - lo > RR_TILE ? end - RR_TILE : lo;
+            u32 best = 0;
+#pragma unroll
+            for (int i = 0; i < RR_ITEMS; ++i) {
+                u32 j = beg + tid + i * RR_BLOCK;
+                if (j < end && (j == 0 || keys[j] != keys[j - 1])) best = pos_base + j + 1;
+            }
+            u32 tot;
+            block_exclusive_max(best, S.tmp, &tot);
+            found = tot;
+            end = beg;
+        }
+        if (tid == 0) st_relaxed(&status[blockIdx.x], found ? (RR_FOUND | (u64)(found - 1)) : RR_NONE);
+    } else {
+        if (tid == 0) st_relaxed(&status[blockIdx.x], RR_NONE);
+        return;
+    }
+    // 2. last head before the range (block 0 owns position 0, which is always a head)
+    if (tid < 32) {
+        u32 pre = 0;
+        int base = (int)blockIdx.x - 1;
+        while (base >= 0) {
+            int t = base - (int)tid;
+            u64 w = RR_NONE;
+            if (t >= 0) do { w = ld_relaxed(&status[t]); } while (w == 0);
+            u32 m = __ballot_sync(FULL_MASK, (w >> 62) == 2);
+            if (m) {
+                pre = __shfl_sync(FULL_MASK, (u32)(w & 0xffffffffu), __ffs(m) - 1);
+                break;
+            }
+            base -= 32;
+        }
+        if (tid == 0) S.tile_prefix = pre;
+    }
+    // 3. the range, tile by tile; the next tile's keys are in flight while the current one is processed
     u64 kreg[RR_ITEMS], kprev = 0, knext = 0;
     auto fetch = [&](u32 t) {
-        if (t >= ntiles) return;
+        if (t >= t1) return;
         const u32 b = t * RR_TILE;
 #pragma unroll
         for (int i = 0; i < RR_ITEMS; ++i) {
@@ -120,15 +170,15 @@ bwt_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, u32 
             knext = b + RR_TILE < n ? keys[b + RR_TILE] : 0;
         }
     };
-    u32 tile = take_ticket(ticket, &S.ticket);
-    fetch(tile);
-    while (tile < ntiles) {
+    fetch(t0);
+    for (u32 tile = t0; tile < t1; ++tile) {
         const u32 base = tile * RR_TILE;
+        __syncthreads();                                           // previous tile's readers are done; S.tile_prefix visible
 #pragma unroll
         for (int i = 0; i < RR_ITEMS; ++i) S.keys[RR_PAD(tid + i * RR_BLOCK + 1)] = kreg[i];
         if (tid == 0) { S.keys[0] = kprev; S.keys[RR_PAD(RR_TILE + 1)] = knext; }
-        const u32 next_tile = take_ticket(ticket, &S.ticket);     // (barriers inside publish S.keys)
-        fetch(next_tile);
+        __syncthreads();
+        fetch(tile + 1);
 
         // blocked: thread owns RR_ITEMS consecutive sorted positions
         u32 loc[RR_ITEMS];
@@ -145,13 +195,8 @@ bwt_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, u32 
         }
         u32 total;
         u32 tprefix = block_exclusive_max(cur, S.tmp, &total);
-        if (tid < 32) {
-            u64 x = lookback_exclusive(status, tile, (u64)total, OpMax());
-            if (tid == 0) S.tile_prefix = (u32)x;
-        }
         if (nheads) atomicAdd(&S.heads, nheads);
         if (nsingle) atomicAdd(&S.singles, nsingle);
-        __syncthreads();
         const u32 pre = max(S.tile_prefix, tprefix);
 
         // ranks + run-aggregated digit histogram (ranks are non-decreasing along sorted order, so
@@ -179,6 +224,7 @@ bwt_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, u32 
         for (int d = 0; d < 4; ++d)
             if (run_c[d]) atomicAdd(&S.hist[d][run_d[d]], run_c[d]);
         __syncthreads();
+        if (tid == 0) S.tile_prefix = max(S.tile_prefix, total);    // carried to the next tile
 
 #pragma unroll
         for (int i = 0; i < RR_ITEMS; ++i) {
@@ -190,7 +236,6 @@ bwt_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, u32 
                 if (rank) rank[sa ? sa[p] : p] = r;          // nullptr: a bucketed scatter follows
             }
         }
-        tile = next_tile;
     }
     __syncthreads();
     for (u32 i = tid; i < 4 * 256; i += RR_BLOCK) {
