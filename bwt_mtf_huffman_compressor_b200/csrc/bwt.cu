@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(RR_BLOCK)
 bwt_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, u32 n, u32 ntiles, u32 pos_base,
                   u32 *__restrict__ rank,
                   u32 *__restrict__ rs, u32 *hist4, u32 *counters /* [0]=groups [1]=singletons */, u64 *status,
-                  u32 *ticket /* unused */)
+                  u32 *block_active /* per block: rotations of its range still in a group > 1 (may be null) */)
 {
     __shared__ RrSmem S;
     const u32 tid = threadIdx.x;
@@ -135,7 +135,10 @@ bwt_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, u32 
         }
         if (tid == 0) st_relaxed(&status[blockIdx.x], found ? (RR_FOUND | (u64)(found - 1)) : RR_NONE);
     } else {
-        if (tid == 0) st_relaxed(&status[blockIdx.x], RR_NONE);
+        if (tid == 0) {
+            st_relaxed(&status[blockIdx.x], RR_NONE);
+            if (block_active) block_active[blockIdx.x] = 0;
+        }
         return;
     }
     // 2. last head before the range (block 0 owns position 0, which is always a head)
@@ -245,6 +248,7 @@ bwt_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, u32 
     if (tid == 0) {
         if (S.heads) atomicAdd(&counters[0], S.heads);
         if (S.singles) atomicAdd(&counters[1], S.singles);
+        if (block_active) block_active[blockIdx.x] = (hi - lo) - S.singles;
     }
 }
 
@@ -271,35 +275,45 @@ __device__ __forceinline__ u32 compact_offset(u32 cnt, u32 tile, u64 *status, u3
 
 // after the last full round: sorted position j is settled iff its group is a singleton, i.e.
 // rs[j] == j and rs[j+1] == j+1.  Survivors keep their order: (start, group rank r1).
-#define CL_ITEMS 16
-#define CL_TILE (AC_BLOCK * CL_ITEMS)
-__global__ void __launch_bounds__(AC_BLOCK)
-bwt_collect_active_kernel(const u32 *__restrict__ rs, const u32 *__restrict__ sa, u32 n, u32 *__restrict__ act_idx,
-                          u32 *__restrict__ act_r1, u64 *status, u32 *ticket)
+// Same contiguous ranges as bwt_rerank_kernel (same grid), whose per-block survivor counts give
+// every block its output offset directly: no look-back, a block scan per tile is all it takes.
+__global__ void __launch_bounds__(RR_BLOCK)
+bwt_collect_active_kernel(const u32 *__restrict__ rs, const u32 *__restrict__ sa, u32 n, u32 ntiles,
+                          const u32 *__restrict__ block_active, u32 *__restrict__ act_idx, u32 *__restrict__ act_r1)
 {
     __shared__ u32 s_tmp[40];
-    __shared__ u32 s_ticket, s_base;
-    const u32 tile = take_ticket(ticket, &s_ticket);
-    const u32 j0 = tile * CL_TILE + threadIdx.x * CL_ITEMS;
-    u32 r[CL_ITEMS + 1];
+    const u32 tid = threadIdx.x;
+    const u32 tpb = (ntiles + gridDim.x - 1) / gridDim.x;
+    const u32 t0 = blockIdx.x * tpb, t1 = min(ntiles, t0 + tpb);
+    if (t0 >= t1) return;
+    u32 part = 0;
+    for (u32 b = tid; b < blockIdx.x; b += RR_BLOCK) part += block_active[b];
+    u32 out;
+    block_exclusive_sum(part, s_tmp, &out);                  // survivors of all earlier ranges
+    for (u32 tile = t0; tile < t1; ++tile) {
+        const u32 j0 = tile * RR_TILE + tid * RR_ITEMS;
+        u32 r[RR_ITEMS + 1];
 #pragma unroll
-    for (int i = 0; i <= CL_ITEMS; ++i) r[i] = j0 + i < n ? rs[j0 + i] : j0 + i;   // past the end counts as a head
-    u32 keep = 0, cnt = 0;
+        for (int i = 0; i <= RR_ITEMS; ++i) r[i] = j0 + i < n ? rs[j0 + i] : j0 + i;   // past the end counts as a head
+        u32 keep = 0, cnt = 0;
 #pragma unroll
-    for (int i = 0; i < CL_ITEMS; ++i) {
-        u32 j = j0 + i;
-        bool k = j < n && !(r[i] == j && r[i + 1] == j + 1);
-        keep |= (u32)k << i;
-        cnt += k;
-    }
-    u32 o = compact_offset(cnt, tile, status, s_tmp, &s_base);
-#pragma unroll
-    for (int i = 0; i < CL_ITEMS; ++i)
-        if ((keep >> i) & 1u) {
-            act_idx[o] = sa ? sa[j0 + i] : j0 + i;
-            act_r1[o] = r[i];
-            ++o;
+        for (int i = 0; i < RR_ITEMS; ++i) {
+            u32 j = j0 + i;
+            bool k = j < n && !(r[i] == j && r[i + 1] == j + 1);
+            keep |= (u32)k << i;
+            cnt += k;
         }
+        u32 total;
+        u32 o = out + block_exclusive_sum(cnt, s_tmp, &total);
+        out += total;
+#pragma unroll
+        for (int i = 0; i < RR_ITEMS; ++i)
+            if ((keep >> i) & 1u) {
+                act_idx[o] = sa ? sa[j0 + i] : j0 + i;
+                act_r1[o] = r[i];
+                ++o;
+            }
+    }
 }
 
 // key[a] = (r1 << 32) | rank[(start + k) mod N] with the eight digit histograms (M is small here)
@@ -488,10 +502,11 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
     u32 *d_hist8 = arena_get<u32>(ctx, 8 * 256);
     const size_t status_u64 = (size_t)(rr_tiles > 2 * ac_tiles_max ? rr_tiles : 2 * ac_tiles_max) + 8;
     u32 *d_rrctl = arena_get<u32>(ctx, 4 * 256 + 8 + 2 * status_u64);
-    const u32 ctiles = (n + CL_TILE - 1) / CL_TILE;
-    // also serves the survivor compaction of the active rounds (<= n/2 elements in AC_TILE tiles)
-    u64 *cstatus = arena_get<u64>(ctx, (size_t)(ctiles > ac_tiles_max ? ctiles : ac_tiles_max) + 4);
-    if (!sb.keys[0] || !sb.keys[1] || !sb.vals[0] || !sb.vals[1] || !d_rank || !d_rs || !d_hist8 || !d_rrctl || !cstatus)
+    // look-back words of the survivor compaction in the active rounds (<= n/2 elements in AC_TILE tiles)
+    u64 *cstatus = arena_get<u64>(ctx, (size_t)ac_tiles_max + 4);
+    u32 *d_bact = arena_get<u32>(ctx, 148 * 6 + 8);
+    const u32 rr_grid = grid_for(rr_tiles, 1, 148 * 6);
+    if (!sb.keys[0] || !sb.keys[1] || !sb.vals[0] || !sb.vals[1] || !d_rank || !d_rs || !d_hist8 || !d_rrctl || !cstatus || !d_bact)
         return bzap_fail(ctx, BZAP_ERR_NOMEM, "bwt scratch");
     u32 *d_hist4 = d_rrctl, *d_counters = d_rrctl + 4 * 256, *d_ticket = d_counters + 4;
     u64 *d_status = (u64 *)(d_rrctl + 4 * 256 + 8);
@@ -520,8 +535,8 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
         CU(ctx, cudaMemsetAsync(d_rrctl, 0, rrctl_bytes, ctx->stream));
         // rank[] is larger than L2 for big blocks: scatter it through a bucketing pass (radix_sort.cu)
         const bool bucketed = sa != nullptr && n > (12u << 20);
-        LAUNCH(ctx, bwt_rerank_kernel, grid_for(rr_tiles, 1, 148 * 6), RR_BLOCK, 0, keys, sa, n, rr_tiles, 0u,
-               bucketed ? (u32 *)nullptr : d_rank, d_rs, d_hist4, d_counters, d_status, d_ticket);
+        LAUNCH(ctx, bwt_rerank_kernel, rr_grid, RR_BLOCK, 0, keys, sa, n, rr_tiles, 0u,
+               bucketed ? (u32 *)nullptr : d_rank, d_rs, d_hist4, d_counters, d_status, d_bact);
         if (bucketed) RET(dev_scatter_perm(ctx, sa, d_rs, n, d_rank, (u32 *)keys, (u32 *)keys + n));
         CU(ctx, cudaMemcpyAsync(h_cnt, d_counters, 2 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -559,8 +574,7 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
         u32 *next_r1 = d_rs + half;
         u32 m = active;
         CU(ctx, cudaMemsetAsync(d_rrctl, 0, rrctl_bytes, ctx->stream));
-        CU(ctx, cudaMemsetAsync(cstatus, 0, ((size_t)ctiles + 2) * sizeof(u64), ctx->stream));
-        LAUNCH(ctx, bwt_collect_active_kernel, ctiles, AC_BLOCK, 0, d_rs, sa, n, ab.vals[0], act_r1, cstatus, d_ticket);
+        LAUNCH(ctx, bwt_collect_active_kernel, rr_grid, RR_BLOCK, 0, d_rs, sa, n, rr_tiles, d_bact, ab.vals[0], act_r1);
         while (true) {
             const u32 mt = (m + AC_TILE - 1) / AC_TILE;
             CU(ctx, cudaMemsetAsync(d_hist8, 0, 8 * 256 * sizeof(u32), ctx->stream));
@@ -622,7 +636,7 @@ int dev_rerank_run(bzap_ctx *ctx, const u64 *d_keys, u32 m, u32 pos_base, u32 *d
     u32 *d_hist4 = d_ctl, *d_counters = d_ctl + 4 * 256, *d_ticket = d_counters + 4;
     u64 *d_status = (u64 *)(d_ctl + 4 * 256 + 8);
     LAUNCH(ctx, bwt_rerank_kernel, grid_for(rr_tiles, 1, 148 * 6), RR_BLOCK, 0, d_keys, (const u32 *)nullptr, m, rr_tiles,
-           pos_base, (u32 *)nullptr, d_rs, d_hist4, d_counters, d_status, d_ticket);
+           pos_base, (u32 *)nullptr, d_rs, d_hist4, d_counters, d_status, (u32 *)nullptr);
     u32 *h = (u32 *)(ctx->mailbox + 1024);
     CU(ctx, cudaMemcpyAsync(h, d_counters, 2 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
