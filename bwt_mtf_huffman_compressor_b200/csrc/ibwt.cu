@@ -46,64 +46,6 @@ __device__ __forceinline__ u32 ib_node_of(u32 row, u32 n, u32 nb, u32 primary)
     return ib_splitter_row(b, n) == row ? b : IB_NIL;
 }
 
-// node[j] = (next << 32) | len ; a regular splitter that coincides with `primary` is dropped
-// (next = NIL, len = 0): node nb covers that row.
-// Sub-list lengths are geometric, so one thread per sub-list would leave most lanes of a warp idle
-// while the longest one finishes.  Instead every lane keeps pulling sub-lists from a global work
-// counter (warp-aggregated, only when >= IB_REFILL lanes are idle): all lanes step until the list
-// of sub-lists is exhausted.
-#define IB_REFILL 8
-__global__ void __launch_bounds__(256)
-ibwt_walk_len_kernel(const u32 *__restrict__ T, u32 n, u32 nb, u32 primary, u64 *__restrict__ node, u32 *counter)
-{
-    const u32 lane = lane_id();
-    u32 j = IB_NIL, row = 0, len = 0;
-    bool exhausted = false;
-    while (true) {
-        const u32 idle = __ballot_sync(FULL_MASK, j == IB_NIL);
-        if (idle == FULL_MASK && exhausted) break;
-        if (!exhausted && __popc(idle) >= IB_REFILL) {
-            const u32 want = (u32)__popc(idle);
-            u32 base = 0;
-            if (lane == 0) base = atomicAdd(counter, want);
-            base = __shfl_sync(FULL_MASK, base, 0);
-            if (j == IB_NIL) {
-                u32 mine = base + (u32)__popc(idle & lanemask_lt());
-                if (mine <= nb) {
-                    row = mine == nb ? primary : ib_splitter_row(mine, n);
-                    if (mine < nb && row == primary) node[mine] = ((u64)IB_NIL << 32);
-                    else { j = mine; len = 0; }
-                }
-            }
-            exhausted = base + want > nb;
-        }
-        if (j != IB_NIL) {
-            row = T[row];
-            ++len;
-            u32 nx = ib_node_of(row, n, nb, primary);
-            if (nx != IB_NIL) {
-                // the list is cut open in front of `primary`: the node that reaches it becomes the tail
-                node[j] = ((u64)(nx == nb ? IB_NIL : nx) << 32) | len;
-                j = IB_NIL;
-            }
-        }
-    }
-}
-
-// one pointer-jumping round: dist[j] += dist[next[j]]; next[j] = next[next[j]]
-__global__ void __launch_bounds__(256) ibwt_wyllie_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, u32 count)
-{
-    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= count) return;
-    u64 a = in[j];
-    u32 nx = (u32)(a >> 32);
-    if (nx != IB_NIL) {
-        u64 b = in[nx];
-        a = (b & 0xffffffff00000000ull) | (u32)((u32)a + (u32)b);
-    }
-    out[j] = a;
-}
-
 // F(r): byte c with cum[c] <= r < cum[c+1].  A 4096-entry coarse table gives the first candidate
 // byte of r's slice; a short forward scan finishes (cum is monotone, 256 steps over N rows).
 #define IB_COARSE_LOG 12
@@ -140,45 +82,109 @@ __device__ __forceinline__ u32 ib_first_col(const FirstCol &F, u32 r)
     return c;
 }
 
-// dist[j] (from the ranking) = bytes from splitter j to the end of the opened list; the list holds
-// cycle_len = dist[nb] bytes, so splitter j starts writing at cycle_len - dist[j].  Same lane
-// refill scheme as ibwt_walk_len_kernel.
+// node[j] = (next << 32) | len ; a regular splitter that coincides with `primary` is dropped
+// (next = NIL, len = 0): node nb covers that row.
+// Sub-list lengths are geometric, so one thread per sub-list would leave most lanes of a warp idle
+// while the longest one finishes.  Instead every lane keeps pulling sub-lists from a global work
+// counter (warp-aggregated, only when >= IB_REFILL lanes are idle): all lanes step until the list
+// of sub-lists is exhausted.
+// The walk already visits every row once, so it also emits the output bytes F(row) -- into a
+// fixed slot of IB_SLOT bytes per sub-list, because the sub-list's place in the output is only
+// known after the ranking.  Sub-lists longer than a slot remember where to resume.
+#define IB_REFILL 8
+#define IB_SLOT 256
 __global__ void __launch_bounds__(256)
-ibwt_walk_write_kernel(const u32 *__restrict__ T, u32 n, u32 nb, u32 primary, const u64 *__restrict__ len_node,
-                       const u64 *__restrict__ ranked, const u32 *__restrict__ cum, u8 *__restrict__ out, u32 *counter)
+ibwt_walk_len_kernel(const u32 *__restrict__ T, u32 n, u32 nb, u32 primary, const u32 *__restrict__ cum,
+                     u64 *__restrict__ node, u8 *__restrict__ slots, u32 *__restrict__ resume, u32 *counter)
 {
     __shared__ FirstCol F;
     ib_first_col_init(F, cum, n);
     const u32 lane = lane_id();
-    const u32 cycle_len = (u32)ranked[nb];
-    u32 row = 0, o = 0, left = 0;
+    u32 j = IB_NIL, row = 0, len = 0;
     bool exhausted = false;
     while (true) {
-        const u32 idle = __ballot_sync(FULL_MASK, left == 0);
+        const u32 idle = __ballot_sync(FULL_MASK, j == IB_NIL);
         if (idle == FULL_MASK && exhausted) break;
         if (!exhausted && __popc(idle) >= IB_REFILL) {
             const u32 want = (u32)__popc(idle);
             u32 base = 0;
             if (lane == 0) base = atomicAdd(counter, want);
             base = __shfl_sync(FULL_MASK, base, 0);
-            if (left == 0) {
+            if (j == IB_NIL) {
                 u32 mine = base + (u32)__popc(idle & lanemask_lt());
                 if (mine <= nb) {
-                    const u64 rk = ranked[mine];
-                    if ((u32)(rk >> 32) == IB_NIL) {          // reaches `primary`: on its cycle
-                        left = (u32)len_node[mine];           // 0 for the dropped duplicate of `primary`
-                        o = cycle_len - (u32)rk;
-                        row = mine == nb ? primary : ib_splitter_row(mine, n);
-                    }
+                    row = mine == nb ? primary : ib_splitter_row(mine, n);
+                    if (mine < nb && row == primary) node[mine] = ((u64)IB_NIL << 32);
+                    else { j = mine; len = 0; }
                 }
             }
             exhausted = base + want > nb;
         }
-        if (left) {
-            out[o++] = (u8)ib_first_col(F, row);              // out[i] = L[T[x_i]] = F(x_i)   (main.cpp:71)
+        if (j != IB_NIL) {
+            if (len < IB_SLOT) slots[(size_t)j * IB_SLOT + len] = (u8)ib_first_col(F, row);   // out[i] = F(x_i), main.cpp:71
+            else if (len == IB_SLOT) resume[j] = row;
             row = T[row];
-            --left;
+            ++len;
+            u32 nx = ib_node_of(row, n, nb, primary);
+            if (nx != IB_NIL) {
+                // the list is cut open in front of `primary`: the node that reaches it becomes the tail
+                node[j] = ((u64)(nx == nb ? IB_NIL : nx) << 32) | len;
+                j = IB_NIL;
+            }
         }
+    }
+}
+
+// one pointer-jumping round: dist[j] += dist[next[j]]; next[j] = next[next[j]]
+__global__ void __launch_bounds__(256) ibwt_wyllie_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, u32 count)
+{
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    u64 a = in[j];
+    u32 nx = (u32)(a >> 32);
+    if (nx != IB_NIL) {
+        u64 b = in[nx];
+        a = (b & 0xffffffff00000000ull) | (u32)((u32)a + (u32)b);
+    }
+    out[j] = a;
+}
+
+// dist[j] (from the ranking) = bytes from splitter j to the end of the opened list; the list holds
+// cycle_len = dist[nb] bytes, so sub-list j belongs at out[cycle_len - dist[j] ...].
+// One warp per sub-list copies its slot; sub-lists on other cycles never reach `primary` and are skipped.
+__global__ void __launch_bounds__(256)
+ibwt_copy_slots_kernel(u32 nb, const u64 *__restrict__ len_node, const u64 *__restrict__ ranked,
+                       const u8 *__restrict__ slots, u8 *__restrict__ out)
+{
+    const u32 j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
+    if (j > nb) return;
+    const u64 rk = ranked[j];
+    if ((u32)(rk >> 32) != IB_NIL) return;
+    const u32 len = min((u32)len_node[j], (u32)IB_SLOT);
+    const u32 o = (u32)ranked[nb] - (u32)rk;
+    const u8 *src = slots + (size_t)j * IB_SLOT;
+    for (u32 t = lane; t < len; t += 32) out[o + t] = src[t];
+}
+
+// the few sub-lists longer than a slot walk on from where the first walk left the slot
+__global__ void __launch_bounds__(256)
+ibwt_overflow_kernel(const u32 *__restrict__ T, u32 n, u32 nb, const u64 *__restrict__ len_node,
+                     const u64 *__restrict__ ranked, const u32 *__restrict__ resume, const u32 *__restrict__ cum,
+                     u8 *__restrict__ out)
+{
+    __shared__ FirstCol F;
+    ib_first_col_init(F, cum, n);
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > nb) return;
+    const u32 len = (u32)len_node[j];
+    if (len <= IB_SLOT) return;
+    const u64 rk = ranked[j];
+    if ((u32)(rk >> 32) != IB_NIL) return;
+    u32 o = (u32)ranked[nb] - (u32)rk + IB_SLOT;
+    u32 row = resume[j];
+    for (u32 t = IB_SLOT; t < len; ++t) {
+        out[o++] = (u8)ib_first_col(F, row);
+        row = T[row];
     }
 }
 
@@ -202,12 +208,15 @@ int dev_ibwt(bzap_ctx *ctx, const u8 *d_last, size_t n64, u64 primary64, u8 *d_o
     u64 *d_len = arena_get<u64>(ctx, nodes);
     u64 *d_rank[2] = {arena_get<u64>(ctx, nodes), arena_get<u64>(ctx, nodes)};
     u32 *d_work = arena_get<u32>(ctx, 8);
-    if (!d_T || !d_cum || !d_len || !d_rank[0] || !d_rank[1] || !d_work) return bzap_fail(ctx, BZAP_ERR_NOMEM, "ibwt scratch");
+    u8 *d_slots = arena_get<u8>(ctx, (size_t)nodes * IB_SLOT);
+    u32 *d_resume = arena_get<u32>(ctx, nodes);
+    if (!d_T || !d_cum || !d_len || !d_rank[0] || !d_rank[1] || !d_work || !d_slots || !d_resume)
+        return bzap_fail(ctx, BZAP_ERR_NOMEM, "ibwt scratch");
     CU(ctx, cudaMemsetAsync(d_work, 0, 8 * sizeof(u32), ctx->stream));
     const u32 wgrid = nodes / 256 + 1 < 148u * 8u ? nodes / 256 + 1 : 148u * 8u;
     RET(dev_sort_positions_by_byte(ctx, d_last, n, d_T, d_cum));
     const u32 nblk = (nodes + 255) / 256;
-    LAUNCH(ctx, ibwt_walk_len_kernel, wgrid, 256, 0, d_T, n, nb, primary, d_len, d_work);
+    LAUNCH(ctx, ibwt_walk_len_kernel, wgrid, 256, 0, d_T, n, nb, primary, d_cum, d_len, d_slots, d_resume, d_work);
     // pointer jumping: after r rounds every node has jumped 2^r links
     int cur = 0;
     const u64 *src = d_len;
@@ -220,7 +229,8 @@ int dev_ibwt(bzap_ctx *ctx, const u8 *d_last, size_t n64, u64 primary64, u8 *d_o
         CU(ctx, cudaMemcpyAsync(d_rank[0], d_len, nodes * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
         src = d_rank[0];
     }
-    LAUNCH(ctx, ibwt_walk_write_kernel, wgrid, 256, 0, d_T, n, nb, primary, d_len, src, d_cum, d_out, d_work + 1);
+    LAUNCH(ctx, ibwt_copy_slots_kernel, (u32)(((size_t)nodes * 32 + 255) / 256), 256, 0, nb, d_len, src, d_slots, d_out);
+    LAUNCH(ctx, ibwt_overflow_kernel, nblk, 256, 0, d_T, n, nb, d_len, src, d_resume, d_cum, d_out);
     u64 *h_cycle = (u64 *)(ctx->mailbox + 1056);
     CU(ctx, cudaMemcpyAsync(h_cycle, src + nb, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
