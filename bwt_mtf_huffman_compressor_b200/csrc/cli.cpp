@@ -7,10 +7,14 @@
 // message on stderr instead of crashing.
 #include "bzap.h"
 #include <cstdio>
+#include <cstring>
 #include <iostream>
 #include <string>
 #include <vector>
 
+#if defined(BZAP_CLI_COMPRESS) && !defined(BZAP_CLI_FULL)
+static void metrics_line(const char *in, const char *out);
+#endif
 static long file_size(const char *p)
 {
     FILE *f = fopen(p, "rb");
@@ -21,6 +25,42 @@ static long file_size(const char *p)
     return s;
 }
 
+#ifdef BZAP_CLI_FULL
+// FULL_PIPELINE mode of the reference (main.cpp:416-438): the 14 Calgary files of calgarycorpus/
+// are compressed, decompressed and compared; "k/14 <metrics line>success|fail" per file.
+static bool same_file(const std::string &a, const std::string &b)
+{
+    FILE *fa = fopen(a.c_str(), "rb"), *fb = fopen(b.c_str(), "rb");
+    bool ok = fa && fb;
+    while (ok) {
+        unsigned char ba[65536], bb[65536];
+        size_t na = fread(ba, 1, sizeof ba, fa), nb = fread(bb, 1, sizeof bb, fb);
+        if (na != nb || memcmp(ba, bb, na) != 0) ok = false;
+        if (na == 0) break;
+    }
+    if (fa) fclose(fa);
+    if (fb) fclose(fb);
+    return ok;
+}
+static void metrics_line(const char *in, const char *out);
+int main(int argc, char *argv[])
+{
+    std::string dir = argc > 1 ? std::string(argv[1]) + "/" : "calgarycorpus/";
+    const char *files[] = {"bib", "book1", "book2", "geo", "news", "obj1", "obj2", "paper1", "paper2",
+                           "pic", "progc", "progl", "progp", "trans"};
+    int failures = 0;
+    for (int k = 0; k < 14; ++k) {
+        std::cout << k + 1 << "/" << 14 << ' ';
+        std::string in = dir + files[k], enc = in + ".bzap", dec = in + ".decoded";
+        int rc = bzap_compress_file(nullptr, in.c_str(), enc.c_str());
+        if (rc == BZAP_OK) { metrics_line(in.c_str(), enc.c_str()); rc = bzap_decompress_file(nullptr, enc.c_str(), dec.c_str()); }
+        bool ok = rc == BZAP_OK && same_file(in, dec);
+        failures += !ok;
+        std::cout << (ok ? "success" : "fail") << std::endl;
+    }
+    return failures ? 2 : 0;
+}
+#else
 int main(int argc, char *argv[])
 {
     if (argc != 3) {
@@ -33,18 +73,7 @@ int main(int argc, char *argv[])
         std::cerr << "bzap_compress: " << bzap_strerror(rc) << ": " << bzap_last_error(nullptr) << std::endl;
         return 2;
     }
-    // metrics line, same arithmetic and formatting as main.cpp:319-323 + print_metrics :402-413
-    long initial = file_size(argv[1]), encoded = file_size(argv[2]);
-    FILE *f = fopen(argv[2], "rb");
-    unsigned char hdr[24] = {0};
-    if (f) { if (fread(hdr, 1, 24, f) != 24) hdr[16] = 0; fclose(f); }
-    unsigned long long tree_bytes = 0;
-    for (int i = 7; i >= 0; --i) tree_bytes = (tree_bytes << 8) | hdr[16 + i];
-    std::cout << "header size: " << double(tree_bytes + 24) << " $$ ";
-    std::cout << "file_name: " << argv[2] << " $$ initial_data_size: " << initial
-              << " $$ encoded_file_size: " << encoded
-              << " $$ bits_avg: " << (8 * double(encoded)) / double(initial)
-              << " $$ compress_rate = " << double(encoded) / double(initial) << std::endl;
+    metrics_line(argv[1], argv[2]);
 #else
     int rc = bzap_decompress_file(nullptr, argv[1], argv[2]);
     if (rc != BZAP_OK) {
@@ -54,3 +83,22 @@ int main(int argc, char *argv[])
 #endif
     return 0;
 }
+#endif
+
+#if defined(BZAP_CLI_COMPRESS) || defined(BZAP_CLI_FULL)
+// metrics line, same arithmetic and formatting as main.cpp:319-323 + print_metrics :402-413
+static void metrics_line(const char *in, const char *out)
+{
+    long initial = file_size(in), encoded = file_size(out);
+    FILE *f = fopen(out, "rb");
+    unsigned char hdr[24] = {0};
+    if (f) { if (fread(hdr, 1, 24, f) != 24) hdr[16] = 0; fclose(f); }
+    unsigned long long tree_bytes = 0;
+    for (int i = 7; i >= 0; --i) tree_bytes = (tree_bytes << 8) | hdr[16 + i];
+    std::cout << "header size: " << double(tree_bytes + 24) << " $$ ";
+    std::cout << "file_name: " << out << " $$ initial_data_size: " << initial
+              << " $$ encoded_file_size: " << encoded
+              << " $$ bits_avg: " << (8 * double(encoded)) / double(initial)
+              << " $$ compress_rate = " << double(encoded) / double(initial) << std::endl;
+}
+#endif

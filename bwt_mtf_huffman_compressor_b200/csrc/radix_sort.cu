@@ -27,6 +27,9 @@
 #ifndef RS_LB_WIDE
 #define RS_LB_WIDE 4
 #endif
+#ifndef SC_VARIANT
+#define SC_VARIANT 1
+#endif
 #ifndef RS_ASYNC_VALS
 #define RS_ASYNC_VALS 0
 #endif
@@ -424,7 +427,19 @@ __global__ void perm_offsets_kernel(u32 n, int shift, u32 *offsets)
 __global__ void __launch_bounds__(256)
 scatter_u32_kernel(const u32 *__restrict__ idx, const u32 *__restrict__ vals, u32 n, u32 *__restrict__ out)
 {
+#if SC_VARIANT == 0
     for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) out[idx[j]] = vals[j];
+#elif SC_VARIANT == 1
+    // streaming loads: the inputs are read once and must not push the half-written target sectors out of L2
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) out[__ldcs(idx + j)] = __ldcs(vals + j);
+#elif SC_VARIANT == 2
+    // contiguous chunk per block: a block stays inside one target window for its whole life
+    const u32 per = (n + gridDim.x - 1) / gridDim.x;
+    const u32 lo = blockIdx.x * per, hi = min(n, lo + per);
+    for (u32 j = lo + threadIdx.x; j < hi; j += blockDim.x) out[__ldcs(idx + j)] = __ldcs(vals + j);
+#elif SC_VARIANT == 3
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) __stwt(out + __ldcs(idx + j), __ldcs(vals + j));
+#endif
 }
 
 int dev_scatter_perm(bzap_ctx *ctx, const u32 *d_perm, const u32 *d_vals, u32 n, u32 *d_out, u32 *d_tmp_idx,

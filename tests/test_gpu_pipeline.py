@@ -203,3 +203,20 @@ def test_cross_decode_with_reference_binaries(name, calgary):
 def test_reference_decodes_our_4m_text():
     d = W.synthetic_text(1 << 22)
     assert_same(O.ref_decompress(bz.compress_bytes(d)), d, "ref decodes ours")
+
+
+def test_full_pipeline_runner(tmp_path, calgary):
+    # FULL_PIPELINE mode of the reference (main.cpp:416-438): k/14 ... success for every file
+    d = tmp_path / "calgarycorpus"
+    d.mkdir()
+    for name, data in calgary.items():
+        (d / name).write_bytes(data)
+    exe = os.path.join(ROOT, "bwt_mtf_huffman_compressor_b200", "bzap_full_pipeline")
+    p = subprocess.run([exe, str(d)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout[-500:] + p.stderr[-500:]
+    lines = p.stdout.strip().split("\n")
+    assert len(lines) == 14
+    for k, (name, line) in enumerate(zip(W.CALGARY_FILES, lines)):
+        assert line.startswith("%d/14 header size: " % (k + 1)) and line.endswith("success"), line
+    # book1 row of the reference README (README.md:24)
+    assert "initial_data_size: 768771 $$ encoded_file_size: 267163 $$ bits_avg: 2.78016 $$ compress_rate = 0.34752" in lines[1]
