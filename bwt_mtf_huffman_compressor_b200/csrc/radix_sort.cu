@@ -27,6 +27,9 @@
 #ifndef RS_LB_WIDE
 #define RS_LB_WIDE 4
 #endif
+#ifndef RS_TWO_CHAINS
+#define RS_TWO_CHAINS 0
+#endif
 #ifndef SC_VARIANT
 #define SC_VARIANT 1
 #endif
@@ -45,6 +48,9 @@ template <typename KeyT, int ITEMS> struct RsSmem {
     KeyT keys[RS_BLOCK * ITEMS];
     u32 vals[RS_BLOCK * ITEMS];
     u32 whist[RS_WARPS][256];
+#if RS_TWO_CHAINS
+    u32 whist2[RS_WARPS][256];         // counters of the second half of each thread's items
+#endif
     u32 adj[256];
     u32 scan_tmp[40];
     u32 ticket;
@@ -107,20 +113,38 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
 
     // warp-level multisplit: rank of each key among the warp's keys with the same digit
     u32 *wh = S.whist[warp];
+#if RS_TWO_CHAINS
+    // The counter update makes consecutive items a dependent chain (match -> read -> write ->
+    // shuffle).  The items are ranked as two independent halves with their own counters, two chains
+    // in flight per warp, and the second half is shifted by the first half's counts afterwards.
+    u32 *wh2 = S.whist2[warp];
+    for (u32 i = lane; i < 256; i += 32) wh2[i] = 0;
+    __syncwarp();
+    constexpr int HALF = ITEMS / 2;
+#pragma unroll
+    for (int j = 0; j < HALF; ++j) {
+        u32 da = digit_of(key[j], shift), db = digit_of(key[j + HALF], shift);
+        u32 ma = __match_any_sync(FULL_MASK, da), mb = __match_any_sync(FULL_MASK, db);
+        u32 la = (u32)__ffs(ma) - 1u, lb = (u32)__ffs(mb) - 1u;
+        u32 pa = 0, pb = 0;
+        if (lane == la) { pa = wh[da]; wh[da] = pa + (u32)__popc(ma); }
+        if (lane == lb) { pb = wh2[db]; wh2[db] = pb + (u32)__popc(mb); }
+        pa = __shfl_sync(FULL_MASK, pa, la);
+        pb = __shfl_sync(FULL_MASK, pb, lb);
+        rnk[j] = pa + (u32)__popc(ma & lanemask_lt());
+        rnk[j + HALF] = pb + (u32)__popc(mb & lanemask_lt());
+        __syncwarp();
+    }
+#pragma unroll
+    for (int j = HALF; j < 2 * HALF; ++j) rnk[j] += wh[digit_of(key[j], shift)];
+    __syncwarp();
+    for (u32 i = lane; i < 256; i += 32) wh[i] += wh2[i];
+    static_assert(ITEMS % 2 == 0, "two ranking chains need an even item count");
+#else
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         u32 d = digit_of(key[j], shift);
         u32 m = __match_any_sync(FULL_MASK, d);
-#if RS_BROADCAST_RANK
-        // every lane of a digit group reads the group's counter (a broadcast), the lowest lane
-        // writes it back: no shuffle, no divergent region
-        u32 below = (u32)__popc(m & lanemask_lt());
-        u32 prev = wh[d];
-        __syncwarp();
-        if (below == 0) wh[d] = prev + (u32)__popc(m);
-        rnk[j] = prev + below;
-        __syncwarp();
-#else
         u32 leader = (u32)__ffs(m) - 1u;
         u32 prev = 0;
         if (lane == leader) {
@@ -130,8 +154,8 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
         prev = __shfl_sync(FULL_MASK, prev, leader);
         rnk[j] = prev + (u32)__popc(m & lanemask_lt());
         __syncwarp();
-#endif
     }
+#endif
     __syncthreads();
 
     // thread b owns digit b: prefix over warps, publish the tile's count, scan over digits
