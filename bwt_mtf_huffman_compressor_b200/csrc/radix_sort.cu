@@ -14,7 +14,9 @@
 // per-pass "trivial" flags; that is what makes periodic inputs (all keys equal) cheap.
 #include "device_common.cuh"
 
+#ifndef RS_BLOCK
 #define RS_BLOCK 256
+#endif
 #ifndef RS_MINBLOCKS
 #define RS_MINBLOCKS 3
 #endif
@@ -159,30 +161,36 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
     __syncthreads();
 
     // thread b owns digit b: prefix over warps, publish the tile's count, scan over digits
-    const u32 bin = tid;
+    const u32 bin = tid & 255u;
+    const bool owner = RS_BLOCK == 256 || tid < 256;    // blocks may be wider than the 256 digit values
     u32 *my_status = status + (size_t)tile * 256 + bin;
-    u32 count, tile_start;
+    u32 count = 0, tile_start;
     {
-        u32 run = 0;
+        if (owner) {
+            u32 run = 0;
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) {
-            u32 t = S.whist[w][bin];
-            S.whist[w][bin] = run;
-            run += t;
+            for (int w = 0; w < RS_WARPS; ++w) {
+                u32 t = S.whist[w][bin];
+                S.whist[w][bin] = run;
+                run += t;
+            }
+            count = run;
+            if (tile == 0) st_relaxed(my_status, RS_FLAG_INCL | count);
+            else st_relaxed(my_status, RS_FLAG_AGG | count);
         }
-        count = run;
-        if (tile == 0) st_relaxed(my_status, RS_FLAG_INCL | count);
-        else st_relaxed(my_status, RS_FLAG_AGG | count);
         u32 total;
         tile_start = block_exclusive_sum(count, S.scan_tmp, &total);
+        if (owner) {
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) S.whist[w][bin] += tile_start;
+            for (int w = 0; w < RS_WARPS; ++w) S.whist[w][bin] += tile_start;
+        }
     }
     // global base of digit `bin`: decoupled look-back over the previous tiles.  It only feeds the
     // final write-out, so (RS_LATE_LOOKBACK) it runs after the shared-memory regroup, which gives
     // the predecessors time to publish their inclusive prefixes; status words are fetched
     // RS_LB_WIDE at a time so that a deep walk is not a chain of dependent L2 round trips.
     auto look_back = [&]() {
+        if (!owner) return;
         u32 excl = 0;
         if (tile > 0) {
             int t = (int)tile - 1;

@@ -1,0 +1,29 @@
+#!/usr/bin/env python
+"""BASELINE config 4: 16 MiB degenerate / periodic blocks -- compress and decompress time per kind."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bwt_mtf_huffman_compressor_b200 as bz
+from bwt_mtf_huffman_compressor_b200 import workloads as W
+n = 1 << 24
+ctx = bz.Context(0)
+rows = {}
+for kind in W.DEGENERATE_KINDS:
+    d = W.degenerate(kind, n)
+    x = torch.from_numpy(d).cuda()
+    out = torch.empty(bz.compress_bound(n), dtype=torch.uint8, device="cuda")
+    back = torch.empty(n, dtype=torch.uint8, device="cuda")
+    best = None
+    for it in range(3):
+        fl = ctx.compress_ptr(x.data_ptr(), n, out.data_ptr(), out.numel(), device=True)
+        s = ctx.stats()
+        ctx.decompress_ptr(out.data_ptr(), fl, back.data_ptr(), n, device=True)
+        sd = ctx.stats()
+        row = (s.ms_total, sd.ms_total, s.bwt_rounds, s.bwt_sort_passes, fl)
+        best = row if best is None or row[0] + row[1] < best[0] + best[1] else best
+    ok = bool(torch.equal(back, x))
+    rows[kind] = {"compress_ms": round(best[0], 3), "decompress_ms": round(best[1], 3), "rounds": best[2], "sort_passes": best[3],
+                  "compressed_bytes": best[4], "compress_MBps": round(n / best[0] / 1e3, 1), "decompress_MBps": round(n / best[1] / 1e3, 1),
+                  "roundtrip_ok": ok}
+    print(kind, rows[kind], flush=True)
+json.dump(rows, open("gpurun_out/degenerate_16m.json", "w"), indent=1)
