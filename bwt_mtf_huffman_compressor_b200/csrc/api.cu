@@ -697,6 +697,14 @@ extern "C" int bzap_dev_scatter_u32(bzap_ctx *ctx, const uint32_t *d_idx, const 
     RESOLVE(ctx);
     return dev_scatter_offset(ctx, d_idx, d_vals, (u32)m, idx_offset, d_out);
 }
+extern "C" int bzap_dev_bucket_by_index(bzap_ctx *ctx, const uint32_t *d_idx, const uint32_t *d_vals, size_t m, int shift,
+                                        uint32_t *d_idx_out, uint32_t *d_vals_out, uint32_t counts[256])
+{
+    if (!d_idx || !d_vals || !d_idx_out || !d_vals_out || !counts || m > BZAP_MAX_BLOCK || shift < 0 || shift > 24) return BZAP_ERR_ARG;
+    if (m == 0) { memset(counts, 0, 256 * sizeof(uint32_t)); return BZAP_OK; }
+    DEV_ENTER(sort_scratch_bytes((u32)m) / 4 + (1u << 20));
+    return dev_bucket_u32(ctx, d_idx, d_vals, (u32)m, shift, d_idx_out, d_vals_out, counts);
+}
 extern "C" int bzap_dev_gather_last(bzap_ctx *ctx, const uint8_t *d_text, size_t n, const uint32_t *d_sa, size_t m, uint8_t *d_last)
 {
     if (!d_text || !d_sa || !d_last || n == 0 || n > BZAP_MAX_BLOCK || m > n) return BZAP_ERR_ARG;

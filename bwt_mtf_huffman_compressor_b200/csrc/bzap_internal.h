@@ -129,6 +129,8 @@ int dev_sort_pairs_generic(bzap_ctx *ctx, u64 *d_keys, u32 *d_vals, u32 m, u64 *
 int dev_permute_pairs(bzap_ctx *ctx, const u64 *d_keys, const u32 *d_vals, const u32 *d_perm, u32 m, u64 *d_out_k, u32 *d_out_v);
 int dev_scatter_offset(bzap_ctx *ctx, const u32 *d_idx, const u32 *d_vals, u32 m, u32 off, u32 *d_out);
 int dev_gather_slots(bzap_ctx *ctx, const u8 *d_text, const u32 *d_sa, u32 n, u32 m, u8 *d_last);
+int dev_bucket_u32(bzap_ctx *ctx, const u32 *d_keys, const u32 *d_vals, u32 m, int shift, u32 *d_keys_out, u32 *d_vals_out,
+                   u32 h_counts[256]);
 int dev_partition_dest(bzap_ctx *ctx, const u64 *d_keys, const u32 *d_vals, u32 m, const u64 *h_sk, const u32 *h_sv, int ns,
                        u8 *d_dest);
 // 256-bin byte histogram accumulated into d_hist256 (caller zeroes it)

@@ -13,6 +13,7 @@
 // Passes whose digit is constant over all keys are skipped on the host after reading back the
 // per-pass "trivial" flags; that is what makes periodic inputs (all keys equal) cheap.
 #include "device_common.cuh"
+#include <cstring>
 
 #ifndef RS_BLOCK
 #define RS_BLOCK 256
@@ -609,5 +610,42 @@ int dev_scatter_offset(bzap_ctx *ctx, const u32 *d_idx, const u32 *d_vals, u32 m
     LAUNCH(ctx, scatter_offset_kernel, min((m + 255) / 256, 148u * 16u), 256, 0, d_idx, d_vals, m, off, d_out);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaGetLastError());
+    return BZAP_OK;
+}
+
+// ---- bucket (index, value) pairs by the top 8 bits of the index (distributed path: ranks go home) --------
+__global__ void __launch_bounds__(256) radix_hist_u32_digit_kernel(const u32 *__restrict__ keys, u32 m, int shift, u32 *hist)
+{
+    __shared__ u32 s_h[256];
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x)
+        atomicAdd(&s_h[(keys[i] >> shift) & 0xffu], 1u);
+    __syncthreads();
+    u32 c = s_h[threadIdx.x];
+    if (c) atomicAdd(&hist[threadIdx.x], c);
+}
+
+int dev_bucket_u32(bzap_ctx *ctx, const u32 *d_keys, const u32 *d_vals, u32 m, int shift, u32 *d_keys_out, u32 *d_vals_out,
+                   u32 h_counts[256])
+{
+    constexpr int ITEMS = RS_ITEMS_32;
+    const u32 tiles = (m + RS_BLOCK * ITEMS - 1) / (RS_BLOCK * ITEMS);
+    const size_t status_words = (size_t)tiles * 256;
+    u32 *d_ctl = arena_get<u32>(ctx, 256 + 264 + 8 + status_words);
+    if (!d_ctl) return bzap_fail(ctx, BZAP_ERR_NOMEM, "bucket scratch");
+    u32 *d_hist = d_ctl, *d_cum = d_ctl + 256, *d_ticket = d_ctl + 520, *d_status = d_ctl + 528;
+    CU(ctx, cudaMemsetAsync(d_ctl, 0, (528 + status_words) * sizeof(u32), ctx->stream));
+    LAUNCH(ctx, radix_hist_u32_digit_kernel, min((m + 255) / 256, 148u * 8u), 256, 0, d_keys, m, shift, d_hist);
+    LAUNCH(ctx, radix_cum_u8_kernel, 1, 256, 0, d_hist, d_cum);
+    auto k = onesweep_pass_kernel<u32, ITEMS, false, true>;
+    const size_t smem = sizeof(RsSmem<u32, ITEMS>);
+    RET(set_smem_attr(ctx, k, smem));
+    LAUNCH(ctx, k, tiles, RS_BLOCK, smem, d_keys, d_keys_out, d_vals, d_vals_out, m, shift, d_cum, d_status, d_ticket);
+    u32 *h = (u32 *)(ctx->mailbox + 28672);
+    CU(ctx, cudaMemcpyAsync(h, d_hist, 256 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaGetLastError());
+    memcpy(h_counts, h, 256 * sizeof(u32));
     return BZAP_OK;
 }

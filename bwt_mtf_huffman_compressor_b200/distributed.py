@@ -23,6 +23,8 @@ suffix-array slots are sharded.  The backend object hides the per-GPU steps so t
 numpy backend; the product only ever uses GpuBackend).
 """
 import ctypes as C
+import os
+import time
 
 import numpy as np
 import torch
@@ -97,6 +99,15 @@ class GpuBackend:
                    self.ctx.h)
         return ok, ov
 
+    def bucket_by_index(self, idx, vals, shift):
+        m = idx.numel()
+        oi, ov = torch.empty_like(idx), torch.empty_like(vals)
+        counts = (C.c_uint32 * 256)()
+        if m:
+            _check(lib().bzap_dev_bucket_by_index(self.ctx.h, C.c_void_p(idx.data_ptr()), C.c_void_p(vals.data_ptr()), m, shift,
+                                                  C.c_void_p(oi.data_ptr()), C.c_void_p(ov.data_ptr()), counts), self.ctx.h)
+        return oi, ov, np.array(counts, dtype=np.int64)
+
     def scatter(self, idx, vals, offset, out):
         if idx.numel():
             _check(lib().bzap_dev_scatter_u32(self.ctx.h, C.c_void_p(idx.data_ptr()), C.c_void_p(vals.data_ptr()), idx.numel(),
@@ -131,15 +142,46 @@ def _install_signatures():
     L.bzap_dev_permute_pairs.argtypes = [vp, vp, vp, vp, sz, vp, vp]
     L.bzap_dev_scatter_u32.argtypes = [vp, vp, vp, sz, C.c_uint32, vp]
     L.bzap_dev_gather_last.argtypes = [vp, vp, sz, vp, sz, vp]
+    L.bzap_dev_bucket_by_index.argtypes = [vp, vp, vp, sz, C.c_int, vp, vp, C.POINTER(C.c_uint32)]
+    L.bzap_dev_bucket_by_index.restype = C.c_int
     for f in ("bzap_dev_permute_pairs", "bzap_dev_scatter_u32", "bzap_dev_gather_last","bzap_dev_init_keys", "bzap_dev_sort_pairs", "bzap_dev_rerank", "bzap_dev_partition_dest",
               "bzap_dev_stable_perm_by_byte", "bzap_compress_from_bwt_device"):
         getattr(L, f).restype = C.c_int
 
 
+# ---- optional phase timing (BZAP_DIST_TIMING=1): wall clock with a device sync per phase ---------------
+_TIMING = os.environ.get("BZAP_DIST_TIMING") == "1"
+_phase = {}
+
+
+def _tick(name, t0, dev):
+    if not _TIMING:
+        return 0.0
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+    t1 = time.perf_counter()
+    _phase[name] = _phase.get(name, 0.0) + (t1 - t0)
+    return t1
+
+
+def phase_times(reset=True):
+    out = dict(_phase)
+    if reset:
+        _phase.clear()
+    return out
+
+
 # ---- host logic --------------------------------------------------------------------------------------
+def index_shift(n):
+    """Bucket digit of an index = (index >> shift) & 255 covers [0, n): shift = bits(n - 1) - 8."""
+    return max(0, (max(n, 1) - 1).bit_length() - 8)
+
+
 def shard_bounds(n, world):
-    """Contiguous text shards of ceil(n / world) positions (the last ones may be short or empty)."""
-    shard = (n + world - 1) // world
+    """Contiguous text shards of about n / world positions, cut at multiples of 2^index_shift(n) so
+    that every 1/256 index bucket has exactly one owner (the last shards may be short or empty)."""
+    unit = 1 << index_shift(n)
+    shard = -(-(-(-n // world)) // unit) * unit
     return shard, [min(n, r * shard) for r in range(world + 1)]
 
 
@@ -206,6 +248,7 @@ def _dist_sort(keys, vals, backend, group, samples_per_rank=256):
     world = dist.get_world_size(group)
     m = keys.numel()
     dev = keys.device
+    t = _tick("", 0, dev) if _TIMING else 0.0
     if world > 1:
         S = samples_per_rank
         if m:
@@ -230,12 +273,17 @@ def _dist_sort(keys, vals, backend, group, samples_per_rank=256):
             split_k, split_v = k_np[cut], v_np[cut]
         else:
             split_k, split_v = np.zeros(0, np.uint64), np.zeros(0, np.uint32)
+        t = _tick("sort.splitters", t, dev)
         dest = backend.partition_dest(keys, vals, split_k, split_v)
         perm, cum = backend.stable_perm_by_byte(dest)
         send_counts = [int(cum[d + 1] - cum[d]) for d in range(world)] if m else [0] * world
         pk, pv = backend.permute_pairs(keys, vals, perm)
+        t = _tick("sort.partition", t, dev)
         (keys, vals), _ = _all_to_all([pk, pv], send_counts, group)
-    return backend.sort_pairs(keys, vals)
+        t = _tick("sort.all_to_all", t, dev)
+    out = backend.sort_pairs(keys, vals)
+    _tick("sort.local", t, dev)
+    return out
 
 
 def _rerank(keys_s, backend, group):
@@ -297,25 +345,32 @@ def distributed_bwt(text, group=None, backend=None):
     k, prev_groups, rounds = 8, 0, 0
     while True:
         keys_s, idx_s = _dist_sort(keys, idx.clone(), backend, group)
+        t = _tick("", 0, dev) if _TIMING else 0.0
         rs, pos_base, groups = _rerank(keys_s, backend, group)
+        t = _tick("rerank", t, dev)
         rounds += 1
-        # ranks go home: (index, rank) to the owner of the index
-        owner = torch.div(idx_s, shard, rounding_mode="floor").to(torch.uint8)
+        # ranks go home: (index, rank) to the owner of the index.  One stable bucketing pass by the
+        # top 8 index bits groups the pairs by owner (shards are cut at bucket boundaries) and leaves
+        # every owner's share ordered by 1/256 window, which keeps its local scatter cache friendly.
         if world > 1:
-            perm, cum = backend.stable_perm_by_byte(owner)
-            send_counts = [int(cum[d + 1] - cum[d]) for d in range(world)] if idx_s.numel() else [0] * world
-            _, pi = backend.permute_pairs(None, idx_s, perm)
-            _, pr = backend.permute_pairs(None, rs, perm)
+            shift = index_shift(n)
+            pi, pr, counts = backend.bucket_by_index(idx_s, rs, shift)
+            send_counts = [0] * world
+            for bkt in range(256):
+                if counts[bkt]:
+                    send_counts[min(world - 1, (bkt << shift) // shard)] += int(counts[bkt])
             (ri, rr), _ = _all_to_all([pi, pr], send_counts, group)
         else:
             ri, rr = idx_s, rs
         backend.scatter(ri, rr, lo, rank_local)
+        t = _tick("ranks_home", t, dev)
         if groups == n or k >= n or groups == prev_groups:
             break
         prev_groups = groups
         r2 = _fetch_shifted(rank_local, n, k, group) if world > 1 else torch.roll(rank_local, -(k % n))
         keys = (rank_local.long() << 32) | r2.long()
         k *= 2
+        _tick("shift+keys", t, dev)
     # last column of this rank's slot range, gathered on rank 0
     last_local = backend.gather_last(text, n, idx_s)
     if world > 1:

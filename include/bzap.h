@@ -158,6 +158,9 @@ int bzap_dev_permute_pairs(bzap_ctx *ctx, const uint64_t *d_keys, const uint32_t
 /* out[idx[j] - idx_offset] = vals[j]  (ranks written back into the owner's shard)                      */
 int bzap_dev_scatter_u32(bzap_ctx *ctx, const uint32_t *d_idx, const uint32_t *d_vals, size_t m, uint32_t idx_offset,
                          uint32_t *d_out);
+/* stable regroup of (index, value) pairs by digit (index >> shift) & 255; counts[256] on the host       */
+int bzap_dev_bucket_by_index(bzap_ctx *ctx, const uint32_t *d_idx, const uint32_t *d_vals, size_t m, int shift,
+                             uint32_t *d_idx_out, uint32_t *d_vals_out, uint32_t counts[256]);
 /* last[j] = text[(sa[j] + n - 1) mod n], j < m  (main.cpp:87 for the slots this GPU holds)             */
 int bzap_dev_gather_last(bzap_ctx *ctx, const uint8_t *d_text, size_t n, const uint32_t *d_sa, size_t m, uint8_t *d_last);
 /* the stages after bwt() (main.cpp:309-324): last column + primary index -> reference-format file    */

@@ -56,6 +56,11 @@ class NumpyBackend:
         p = perm.long()
         return (None if keys is None else keys[p]), vals[p]
 
+    def bucket_by_index(self, idx, vals, shift):
+        d = (idx.numpy().astype(np.int64) >> shift) & 255
+        o = np.argsort(d, kind="stable")
+        return idx[torch.from_numpy(o)], vals[torch.from_numpy(o)], np.bincount(d, minlength=256).astype(np.int64)
+
     def scatter(self, idx, vals, offset, out):
         out[(idx - offset).long()] = vals
 

@@ -23,6 +23,7 @@ best = None
 for it in range(a.reps + 1):
     dist.barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
+    D.phase_times()
     blob, rounds = D.compress_block_distributed(text, None, backend)
     torch.cuda.synchronize(); dist.barrier()
     dt = time.perf_counter() - t0
@@ -34,6 +35,8 @@ if rank == 0:
     line = {"workload": "one %d-byte text block, distributed prefix doubling" % a.size, "n_gpus": world, "rounds": rounds,
             "seconds": round(float(t[0]), 4), "MBps": round(a.size / float(t[0]) / 1e6, 1), "compressed_bytes": int(blob.numel()),
             "sha256": hashlib.sha256(blob.cpu().numpy().tobytes()).hexdigest()}
+    if os.environ.get("BZAP_DIST_TIMING") == "1":
+        line["phase_seconds_last_rep_rank0"] = {k: round(v, 4) for k, v in D.phase_times().items() if k}
     if a.check:
         ref = bz.compress_bytes(data)
         line["equals_single_gpu_path"] = bool(np.array_equal(ref, blob.cpu().numpy()))
