@@ -519,6 +519,11 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
     LAUNCH(ctx, bwt_spread_hist_kernel, 1, 256, 0, d_hist4, 1, d_hist8);
     LAUNCH(ctx, bwt_init_keys_kernel, grid_for((n + IK_TILE - 1) / IK_TILE, 1, 148 * 8), IK_BLOCK, 0, d_in, n, 0u, n, sb.keys[0]);
 
+    // digits of (rank << 32 | rank) that can differ at all: ranks are < n
+    u32 rank_bits = 1;
+    while (rank_bits < 32 && (1ull << rank_bits) < n) ++rank_bits;
+    const u32 nd = (rank_bits + 7) / 8;
+    const u32 rank_mask = ((1u << nd) - 1u) | (((1u << nd) - 1u) << 4);
     u64 *keys = nullptr;
     u32 *sa = nullptr;
     u32 rounds = 0, passes_total = 0, prev_groups = 0;
@@ -530,7 +535,7 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
     while (true) {
         int passes = 0;
         ctx->arena_off = arena_mark;             // sort control block is per round
-        RET(dev_sort_pairs64(ctx, &sb, n, 64, d_hist8, true, &keys, &sa, &passes));
+        RET(dev_sort_pairs64(ctx, &sb, n, rounds == 0 ? 0xffu : rank_mask, d_hist8, true, &keys, &sa, &passes));
         passes_total += (u32)passes;
         CU(ctx, cudaMemsetAsync(d_rrctl, 0, rrctl_bytes, ctx->stream));
         // rank[] is larger than L2 for big blocks: scatter it through a bucketing pass (radix_sort.cu)
@@ -584,7 +589,7 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
             u64 *skeys = nullptr;
             u32 *sidx = nullptr;
             ctx->arena_off = arena_mark;
-            RET(dev_sort_pairs64(ctx, &ab, m, 64, d_hist8, false, &skeys, &sidx, &passes));
+            RET(dev_sort_pairs64(ctx, &ab, m, rank_mask, d_hist8, false, &skeys, &sidx, &passes));
             passes_total += (u32)passes;
             CU(ctx, cudaMemsetAsync(d_rrctl, 0, rrctl_bytes, ctx->stream));
             LAUNCH(ctx, bwt_active_rerank_kernel, mt, AC_BLOCK, 0, skeys, sidx, m, sa_buf, d_rank, newr, pos, d_counters,

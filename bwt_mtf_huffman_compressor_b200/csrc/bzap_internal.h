@@ -106,8 +106,9 @@ int dev_huff_decode(bzap_ctx *ctx, const u8 *d_payload, size_t payload_len, cons
 int dev_ibwt(bzap_ctx *ctx, const u8 *d_last, size_t n, u64 primary, u8 *d_out);
 
 // ---- radix sort building blocks (radix_sort.cu) ----------------------------------------------
-// LSD onesweep over `nbits` low bits of 64-bit keys with 32-bit payloads.  d_hist holds
-// ceil(nbits/8) x 256 digit counts already accumulated by the caller's key-producing kernel.
+// LSD onesweep over 64-bit keys with 32-bit payloads.  d_hist holds 8 x 256 digit counts already
+// accumulated by the caller's key-producing kernel; pass_mask bit p = digit p can vary at all (used
+// instead of a flag read-back for small inputs, where a host round trip costs more than a pass).
 // vals_in == nullptr means "payload = element index" (materialised by the first executed pass).
 // On return *out_keys / *out_vals point at the buffers holding the result (vals may be nullptr
 // when no pass executed and the payload is still the identity).
@@ -115,7 +116,7 @@ struct SortBuffers {
     u64 *keys[2];
     u32 *vals[2];
 };
-int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, int nbits, u32 *d_hist, bool vals_are_iota,
+int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, u32 pass_mask, u32 *d_hist, bool vals_are_iota,
                      u64 **out_keys, u32 **out_vals, int *passes_run);
 // stable counting sort of positions by byte value: T[r] = position of the r-th smallest (byte, pos)
 // (main.cpp:67); d_cum receives the 257 exclusive byte counts

@@ -253,22 +253,28 @@ int dev_huff_decode(bzap_ctx *ctx, const u8 *d_payload, size_t payload_len, cons
     CU(ctx, cudaMemsetAsync(d_dirty[1], 0, nsub, ctx->stream));
     CU(ctx, cudaMemsetAsync(d_count, 0, nsub * sizeof(u32), ctx->stream));
     const size_t smem = sizeof(DecSmem);
-    CU(ctx, cudaFuncSetAttribute(huff_dec_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(ctx, cudaFuncSetAttribute(huff_dec_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static_assert(sizeof(DecSmem) <= 48 * 1024, "decoder shared memory must fit the default dynamic limit");
 
     u32 *h_changed = (u32 *)(ctx->mailbox + 1040);
     int cur = 0;
     u32 iters = 0;
+    // The first sweeps are issued back to back (typical streams settle in two; the third only
+    // confirms, and touches no block without a dirty subsequence); the host looks at the flag of
+    // the last one and keeps sweeping, one round trip each, only if something still moved.
+    const u32 burst = nsub > 1 ? 3 : 1;
     while (true) {
-        CU(ctx, cudaMemsetAsync(d_changed, 0, sizeof(u32), ctx->stream));
-        LAUNCH(ctx, huff_dec_sync_kernel, blocks, DEC_BLOCK, smem, (const u32 *)d_payload, total_words, payload_bits,
-               d_tables, nsub, d_start[cur], d_dirty[cur], d_start[cur ^ 1], d_dirty[cur ^ 1], d_count, d_changed);
+        const u32 todo = iters == 0 ? burst : 1;
+        for (u32 q = 0; q < todo; ++q) {
+            CU(ctx, cudaMemsetAsync(d_changed, 0, sizeof(u32), ctx->stream));
+            LAUNCH(ctx, huff_dec_sync_kernel, blocks, DEC_BLOCK, smem, (const u32 *)d_payload, total_words, payload_bits,
+                   d_tables, nsub, d_start[cur], d_dirty[cur], d_start[cur ^ 1], d_dirty[cur ^ 1], d_count, d_changed);
+            cur ^= 1;
+            ++iters;
+        }
         CU(ctx, cudaMemcpyAsync(h_changed, d_changed, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
-        cur ^= 1;
-        ++iters;
         if (!*h_changed) break;
-        if (iters > nsub + 2) return bzap_fail(ctx, BZAP_ERR_CORRUPT, "decoder did not reach a fixed point");
+        if (iters > nsub + 4) return bzap_fail(ctx, BZAP_ERR_CORRUPT, "decoder did not reach a fixed point");
     }
     ctx->stats.decode_sync_iters = iters;
     CU(ctx, cudaMemsetAsync(d_status, 0, ((size_t)sc_tiles + 2) * sizeof(u64), ctx->stream));

@@ -244,7 +244,8 @@ int dev_huff_encode(bzap_ctx *ctx, const u8 *d_in, size_t n64, const CodeTable *
     if (smem > 200 * 1024) return bzap_fail(ctx, BZAP_ERR_TOO_LARGE, "code length %d", ct->max_len);
     // the attribute is per function, not per launch: contexts on other threads (batch API) may need
     // a different size at the same time, so it is raised once to the largest size ever accepted
-    CU(ctx, cudaFuncSetAttribute(huff_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if (smem > 40 * 1024)
+        CU(ctx, cudaFuncSetAttribute(huff_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     LAUNCH(ctx, huff_encode_kernel, tiles, ENC_BLOCK, smem, d_in, n, d_table, (u32 *)d_file, bit_base, d_status, d_ticket,
            words);
     CU(ctx, cudaGetLastError());

@@ -33,6 +33,9 @@
 #ifndef RS_TWO_CHAINS
 #define RS_TWO_CHAINS 0
 #endif
+#ifndef RS_SMALL_N
+#define RS_SMALL_N (1u << 19)
+#endif
 #ifndef SC_VARIANT
 #define SC_VARIANT 1
 #endif
@@ -350,11 +353,11 @@ template <typename K> static int set_smem_attr(bzap_ctx *ctx, K kernel, size_t b
     return BZAP_OK;
 }
 
-int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, int nbits, u32 *d_hist, bool vals_are_iota, u64 **out_keys,
+int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, u32 pass_mask, u32 *d_hist, bool vals_are_iota, u64 **out_keys,
                      u32 **out_vals, int *passes_run)
 {
     constexpr int ITEMS = RS_ITEMS_64;
-    const int passes = (nbits + 7) / 8;
+    const int passes = 8;
     const u32 tiles = (n + RS_BLOCK * ITEMS - 1) / (RS_BLOCK * ITEMS);
     const size_t status_words = (size_t)tiles * 256;
     // control block: offsets[8][256], trivial[8], tickets[8], then status per pass
@@ -364,8 +367,14 @@ int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, int nbits, u32 *d_his
     CU(ctx, cudaMemsetAsync(d_trivial, 0, (16 + passes * status_words) * sizeof(u32), ctx->stream));
     LAUNCH(ctx, radix_offsets_kernel, 1, 256, 0, d_hist, d_offsets, d_trivial, n, passes);
     u32 *h_trivial = (u32 *)ctx->mailbox;
-    CU(ctx, cudaMemcpyAsync(h_trivial, d_trivial, 8 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n <= RS_SMALL_N) {
+        // small inputs are launch / sync latency bound: a host round trip to learn which passes are
+        // trivial costs more than simply running them (a trivial pass is the identity permutation)
+        for (int p = 0; p < 8; ++p) h_trivial[p] = !((pass_mask >> p) & 1u);     // digits that can vary at all
+    } else {
+        CU(ctx, cudaMemcpyAsync(h_trivial, d_trivial, 8 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
 
     auto k_iota = onesweep_pass_kernel<u64, ITEMS, true, true>;
     auto k_vals = onesweep_pass_kernel<u64, ITEMS, false, true>;
@@ -534,7 +543,7 @@ int dev_sort_pairs_generic(bzap_ctx *ctx, u64 *d_keys, u32 *d_vals, u32 m, u64 *
     u64 *ok = nullptr;
     u32 *ov = nullptr;
     int passes = 0;
-    RET(dev_sort_pairs64(ctx, &sb, m, 64, d_hist8, false, &ok, &ov, &passes));
+    RET(dev_sort_pairs64(ctx, &sb, m, 0xffu, d_hist8, false, &ok, &ov, &passes));
     *result_in_tmp = ok == d_keys_tmp;
     return BZAP_OK;
 }

@@ -214,9 +214,11 @@ def test_full_pipeline_runner(tmp_path, calgary):
     exe = os.path.join(ROOT, "bwt_mtf_huffman_compressor_b200", "bzap_full_pipeline")
     p = subprocess.run([exe, str(d)], capture_output=True, text=True)
     assert p.returncode == 0, p.stdout[-500:] + p.stderr[-500:]
+    # per file: "k/14 <metrics line>\n" (print_metrics ends the line, main.cpp:412) then "success\n" (:436)
     lines = p.stdout.strip().split("\n")
-    assert len(lines) == 14
-    for k, (name, line) in enumerate(zip(W.CALGARY_FILES, lines)):
-        assert line.startswith("%d/14 header size: " % (k + 1)) and line.endswith("success"), line
+    assert len(lines) == 28
+    for k in range(14):
+        assert lines[2 * k].startswith("%d/14 header size: " % (k + 1)), lines[2 * k]
+        assert lines[2 * k + 1] == "success"
     # book1 row of the reference README (README.md:24)
-    assert "initial_data_size: 768771 $$ encoded_file_size: 267163 $$ bits_avg: 2.78016 $$ compress_rate = 0.34752" in lines[1]
+    assert "initial_data_size: 768771 $$ encoded_file_size: 267163 $$ bits_avg: 2.78016 $$ compress_rate = 0.34752" in lines[2]
