@@ -222,3 +222,41 @@ def test_full_pipeline_runner(tmp_path, calgary):
         assert lines[2 * k + 1] == "success"
     # book1 row of the reference README (README.md:24)
     assert "initial_data_size: 768771 $$ encoded_file_size: 267163 $$ bits_avg: 2.78016 $$ compress_rate = 0.34752" in lines[2]
+
+
+def test_unaligned_device_pointers_and_capacity_errors():
+    import torch
+    d = W.synthetic_text(300001)
+    want = O.o_compress(d)
+    ctx = bz.Context()
+    buf = torch.zeros(d.size + 64, dtype=torch.uint8, device="cuda")
+    for off in (1, 3, 8):                                      # input not 16-byte aligned
+        buf[off:off + d.size] = torch.from_numpy(d).cuda()
+        out = torch.empty(bz.compress_bound(d.size) + 32, dtype=torch.uint8, device="cuda")
+        n = ctx.compress_ptr(buf.data_ptr() + off, d.size, out.data_ptr() + off, bz.compress_bound(d.size), device=True)
+        assert_same(out[off:off + n].cpu().numpy(), want, "unaligned off=%d" % off)
+        back = torch.empty(d.size + 32, dtype=torch.uint8, device="cuda")
+        m = ctx.decompress_ptr(out.data_ptr() + off, n, back.data_ptr() + off, d.size, device=True)
+        assert m == d.size
+        assert_same(back[off:off + m].cpu().numpy(), d, "unaligned decompress off=%d" % off)
+    # output capacity too small -> BZAP_ERR_CAPACITY, nothing crashes
+    out = np.empty(100, dtype=np.uint8)
+    with pytest.raises(bz.BzapError) as e:
+        ctx.compress_ptr(d.ctypes.data, d.size, out.ctypes.data, out.size)
+    assert e.value.code == bz.ERR_CAPACITY
+    small = np.empty(10, dtype=np.uint8)
+    with pytest.raises(bz.BzapError) as e:
+        ctx.decompress_ptr(want.ctypes.data, want.size, small.ctypes.data, small.size)
+    assert e.value.code == bz.ERR_CAPACITY
+    # a header announcing N = 0 decodes to nothing
+    empty = np.zeros(27, dtype=np.uint8)
+    empty[16] = 2
+    assert bz.decompress_bytes(empty).size == 0
+
+
+def test_payload_shorter_than_header_claims():
+    blob = bz.compress_bytes(W.synthetic_text(200000))
+    cut = blob[: blob.size - 2000].copy()                      # payload truncated: N code words cannot be there
+    with pytest.raises(bz.BzapError) as e:
+        bz.decompress_bytes(cut)
+    assert e.value.code == bz.ERR_CORRUPT
