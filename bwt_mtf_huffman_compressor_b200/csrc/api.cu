@@ -697,6 +697,13 @@ extern "C" int bzap_dev_scatter_u32(bzap_ctx *ctx, const uint32_t *d_idx, const 
     RESOLVE(ctx);
     return dev_scatter_offset(ctx, d_idx, d_vals, (u32)m, idx_offset, d_out);
 }
+extern "C" int bzap_dev_bwt_finish(bzap_ctx *ctx, const uint8_t *d_text, size_t n, uint32_t *d_sa, uint32_t *d_rank, uint32_t *d_rs,
+                                   uint64_t k, uint8_t *d_last, uint64_t *primary)
+{
+    if (!d_text || !d_sa || !d_rank || !d_rs || !d_last || !primary || n == 0 || n > BZAP_MAX_BLOCK) return BZAP_ERR_ARG;
+    DEV_ENTER(22 * n + sort_scratch_bytes((u32)(n / 2 + 1)) + (8u << 20));
+    return dev_bwt_finish(ctx, d_text, (u32)n, d_sa, d_rank, d_rs, k, d_last, primary);
+}
 extern "C" int bzap_dev_bucket_by_index(bzap_ctx *ctx, const uint32_t *d_idx, const uint32_t *d_vals, size_t m, int shift,
                                         uint32_t *d_idx_out, uint32_t *d_vals_out, uint32_t counts[256])
 {

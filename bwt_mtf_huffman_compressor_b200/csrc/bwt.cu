@@ -479,6 +479,87 @@ static inline u32 grid_for(size_t work_items, u32 per_block, u32 cap = 148u * 16
     return (u32)(g > cap ? cap : g);
 }
 
+// ---- active rounds, host loop ------------------------------------------------------------------------------
+struct ActiveWork {
+    SortBuffers ab;                       // key / payload ping-pong buffers for up to m elements
+    u32 *act_r1, *newr, *pos;             // per active element: group rank, new rank, suffix-array slot
+    u32 *next_idx, *next_r1;              // survivors of a round
+    u32 *sa_buf, *d_rank;                 // the block's suffix array and text-order ranks (updated in place)
+    u32 *d_hist8, *d_rrctl;
+    size_t rrctl_bytes;
+    u32 *d_counters, *d_ticket;
+    u64 *d_status, *cstatus;
+    size_t arena_mark;
+    u32 rank_mask;
+};
+
+// w.ab.vals[0] / w.act_r1 hold the m unsettled rotations (start, group rank) in suffix-array order;
+// ranks reflect prefixes of length *k
+static int bwt_active_rounds(bzap_ctx *ctx, u32 n, u32 m, u64 *k_io, const ActiveWork &w, u32 *rounds, u32 *passes_total)
+{
+    u64 k = *k_io;
+    u32 *h_cnt = (u32 *)(ctx->mailbox + 1024);
+    SortBuffers ab = w.ab;
+    while (m) {
+        const u32 mt = (m + AC_TILE - 1) / AC_TILE;
+        CU(ctx, cudaMemsetAsync(w.d_hist8, 0, 8 * 256 * sizeof(u32), ctx->stream));
+        LAUNCH(ctx, bwt_active_keys_kernel, grid_for(m, 256, 148 * 4), 256, 0, ab.vals[0], w.act_r1, m, w.d_rank, n,
+               (u32)(k % n), ab.keys[0], w.d_hist8);
+        int passes = 0;
+        u64 *skeys = nullptr;
+        u32 *sidx = nullptr;
+        ctx->arena_off = w.arena_mark;
+        RET(dev_sort_pairs64(ctx, &ab, m, w.rank_mask, w.d_hist8, false, &skeys, &sidx, &passes));
+        *passes_total += (u32)passes;
+        CU(ctx, cudaMemsetAsync(w.d_rrctl, 0, w.rrctl_bytes, ctx->stream));
+        LAUNCH(ctx, bwt_active_rerank_kernel, mt, AC_BLOCK, 0, skeys, sidx, m, w.sa_buf, w.d_rank, w.newr, w.pos, w.d_counters,
+               w.d_status, w.d_status + mt + 2, w.d_ticket);
+        CU(ctx, cudaMemsetAsync(w.cstatus, 0, ((size_t)mt + 2) * sizeof(u64), ctx->stream));
+        LAUNCH(ctx, bwt_active_compact_kernel, mt, AC_BLOCK, 0, w.newr, w.pos, sidx, m, w.next_idx, w.next_r1, w.d_counters + 2,
+               w.cstatus, w.d_ticket + 1);
+        CU(ctx, cudaMemcpyAsync(h_cnt, w.d_counters, 3 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        ++*rounds;
+        k *= 2;
+        const u32 groups = h_cnt[0], subgroups = h_cnt[1], m2 = h_cnt[2];
+        if (m2 == 0 || k >= n || subgroups == groups) break;
+        // survivors become the next round's input (copy into the sort's payload buffer 0)
+        CU(ctx, cudaMemcpyAsync(ab.vals[0], w.next_idx, (size_t)m2 * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(w.act_r1, w.next_r1, (size_t)m2 * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+        m = m2;
+    }
+    *k_io = k;
+    return BZAP_OK;
+}
+
+// per-range survivor counts for bwt_collect_active_kernel when the re-rank kernel did not run here
+__global__ void __launch_bounds__(RR_BLOCK)
+bwt_count_active_kernel(const u32 *__restrict__ rs, u32 n, u32 ntiles, u32 *__restrict__ block_active, u32 *total)
+{
+    __shared__ u32 s_tmp[40];
+    const u32 tid = threadIdx.x;
+    const u32 tpb = (ntiles + gridDim.x - 1) / gridDim.x;
+    const u32 t0 = blockIdx.x * tpb, t1 = min(ntiles, t0 + tpb);
+    u32 cnt = 0;
+    for (u32 tile = t0; tile < t1; ++tile) {
+        const u32 j0 = tile * RR_TILE + tid * RR_ITEMS;
+#pragma unroll
+        for (int i = 0; i < RR_ITEMS; ++i) {
+            u32 j = j0 + i;
+            if (j < n) {
+                u32 r0 = rs[j], r1 = j + 1 < n ? rs[j + 1] : j + 1;
+                cnt += !(r0 == j && r1 == j + 1);
+            }
+        }
+    }
+    u32 tot;
+    block_exclusive_sum(cnt, s_tmp, &tot);
+    if (tid == 0) {
+        block_active[blockIdx.x] = tot;
+        if (tot) atomicAdd(total, tot);
+    }
+}
+
 int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
 {
     if (n64 == 0) return bzap_fail(ctx, BZAP_ERR_EMPTY, "empty input");
@@ -577,37 +658,14 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
         u32 *act_r1 = scratch, *newr = scratch + half, *pos = scratch + 2 * (size_t)half;
         u32 *next_idx = d_rs;                                  // rs is dead once the survivors are collected
         u32 *next_r1 = d_rs + half;
-        u32 m = active;
         CU(ctx, cudaMemsetAsync(d_rrctl, 0, rrctl_bytes, ctx->stream));
         LAUNCH(ctx, bwt_collect_active_kernel, rr_grid, RR_BLOCK, 0, d_rs, sa, n, rr_tiles, d_bact, ab.vals[0], act_r1);
-        while (true) {
-            const u32 mt = (m + AC_TILE - 1) / AC_TILE;
-            CU(ctx, cudaMemsetAsync(d_hist8, 0, 8 * 256 * sizeof(u32), ctx->stream));
-            LAUNCH(ctx, bwt_active_keys_kernel, grid_for(m, 256, 148 * 4), 256, 0, ab.vals[0], act_r1, m, d_rank, n,
-                   (u32)(k % n), ab.keys[0], d_hist8);
-            int passes = 0;
-            u64 *skeys = nullptr;
-            u32 *sidx = nullptr;
-            ctx->arena_off = arena_mark;
-            RET(dev_sort_pairs64(ctx, &ab, m, rank_mask, d_hist8, false, &skeys, &sidx, &passes));
-            passes_total += (u32)passes;
-            CU(ctx, cudaMemsetAsync(d_rrctl, 0, rrctl_bytes, ctx->stream));
-            LAUNCH(ctx, bwt_active_rerank_kernel, mt, AC_BLOCK, 0, skeys, sidx, m, sa_buf, d_rank, newr, pos, d_counters,
-                   d_status, d_status + mt + 2, d_ticket);
-            CU(ctx, cudaMemsetAsync(cstatus, 0, ((size_t)mt + 2) * sizeof(u64), ctx->stream));
-            LAUNCH(ctx, bwt_active_compact_kernel, mt, AC_BLOCK, 0, newr, pos, sidx, m, next_idx, next_r1, d_counters + 2,
-                   cstatus, d_ticket + 1);
-            CU(ctx, cudaMemcpyAsync(h_cnt, d_counters, 3 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
-            CU(ctx, cudaStreamSynchronize(ctx->stream));
-            ++rounds;
-            k *= 2;
-            const u32 groups = h_cnt[0], subgroups = h_cnt[1], m2 = h_cnt[2];
-            if (m2 == 0 || k >= n || subgroups == groups) break;
-            // survivors become the next round's input (copy into the sort's payload buffer 0)
-            CU(ctx, cudaMemcpyAsync(ab.vals[0], next_idx, (size_t)m2 * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
-            CU(ctx, cudaMemcpyAsync(act_r1, next_r1, (size_t)m2 * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
-            m = m2;
-        }
+        ActiveWork w;
+        w.ab = ab; w.act_r1 = act_r1; w.newr = newr; w.pos = pos; w.next_idx = next_idx; w.next_r1 = next_r1;
+        w.sa_buf = sa_buf; w.d_rank = d_rank; w.d_hist8 = d_hist8; w.d_rrctl = d_rrctl; w.rrctl_bytes = rrctl_bytes;
+        w.d_counters = d_counters; w.d_ticket = d_ticket; w.d_status = d_status; w.cstatus = cstatus;
+        w.arena_mark = arena_mark; w.rank_mask = rank_mask;
+        RET(bwt_active_rounds(ctx, n, active, &k, w, &rounds, &passes_total));
         sa = sa_buf;
     }
     LAUNCH(ctx, bwt_gather_kernel, grid_for((n + 3) / 4, 256), 256, 0, d_in, sa, n, d_last);
@@ -665,5 +723,67 @@ int dev_gather_slots(bzap_ctx *ctx, const u8 *d_text, const u32 *d_sa, u32 n, u3
     LAUNCH(ctx, bwt_gather_slots_kernel, grid_for(m, 256), 256, 0, d_text, d_sa, n, m, d_last);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaGetLastError());
+    return BZAP_OK;
+}
+
+// Finishes a BWT whose first rounds were done elsewhere (the distributed path hands over once few
+// rotations are unsettled): d_sa = suffix array so far, d_rs = sparse ranks in suffix-array order,
+// d_rank = the same ranks in text order, all for prefix length k.  Runs active rounds to the end,
+// then writes the last column.  d_rs is clobbered.
+int dev_bwt_finish(bzap_ctx *ctx, const u8 *d_text, u32 n, u32 *d_sa, u32 *d_rank, u32 *d_rs, u64 k, u8 *d_last, u64 *primary)
+{
+    const u32 rr_tiles = (n + RR_TILE - 1) / RR_TILE;
+    const u32 rr_grid = grid_for(rr_tiles, 1, 148 * 6);
+    u32 *d_bact = arena_get<u32>(ctx, 148 * 6 + 8);
+    if (!d_bact) return bzap_fail(ctx, BZAP_ERR_NOMEM, "bwt scratch");
+    u32 *d_total = d_bact + 148 * 6 + 2;
+    CU(ctx, cudaMemsetAsync(d_total, 0, sizeof(u32), ctx->stream));
+    LAUNCH(ctx, bwt_count_active_kernel, rr_grid, RR_BLOCK, 0, d_rs, n, rr_tiles, d_bact, d_total);
+    u32 *h_cnt = (u32 *)(ctx->mailbox + 1024);
+    CU(ctx, cudaMemcpyAsync(h_cnt, d_total, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    const u32 m = h_cnt[0];
+    u32 rounds = 0, passes_total = 0;
+    if (m && k < n) {
+        const u32 mt = (m + AC_TILE - 1) / AC_TILE;
+        ActiveWork w;
+        w.ab.keys[0] = arena_get<u64>(ctx, m);
+        w.ab.keys[1] = arena_get<u64>(ctx, m);
+        w.ab.vals[0] = arena_get<u32>(ctx, m);
+        w.ab.vals[1] = arena_get<u32>(ctx, m);
+        w.act_r1 = arena_get<u32>(ctx, m);
+        w.newr = arena_get<u32>(ctx, m);
+        w.pos = arena_get<u32>(ctx, m);
+        w.next_idx = arena_get<u32>(ctx, m);
+        w.next_r1 = arena_get<u32>(ctx, m);
+        w.d_hist8 = arena_get<u32>(ctx, 8 * 256);
+        const size_t status_u64 = 2 * ((size_t)mt + 2) + 8;
+        w.d_rrctl = arena_get<u32>(ctx, 4 * 256 + 8 + 2 * status_u64);
+        w.cstatus = arena_get<u64>(ctx, (size_t)mt + 4);
+        if (!w.ab.keys[0] || !w.ab.keys[1] || !w.ab.vals[0] || !w.ab.vals[1] || !w.act_r1 || !w.newr || !w.pos || !w.next_idx ||
+            !w.next_r1 || !w.d_hist8 || !w.d_rrctl || !w.cstatus)
+            return bzap_fail(ctx, BZAP_ERR_NOMEM, "bwt scratch");
+        w.rrctl_bytes = (4 * 256 + 8 + 2 * status_u64) * sizeof(u32);
+        w.d_counters = w.d_rrctl + 4 * 256;
+        w.d_ticket = w.d_counters + 4;
+        w.d_status = (u64 *)(w.d_rrctl + 4 * 256 + 8);
+        w.sa_buf = d_sa;
+        w.d_rank = d_rank;
+        w.arena_mark = ctx->arena_off;
+        u32 rank_bits = 1;
+        while (rank_bits < 32 && (1ull << rank_bits) < n) ++rank_bits;
+        const u32 nd = (rank_bits + 7) / 8;
+        w.rank_mask = ((1u << nd) - 1u) | (((1u << nd) - 1u) << 4);
+        LAUNCH(ctx, bwt_collect_active_kernel, rr_grid, RR_BLOCK, 0, d_rs, d_sa, n, rr_tiles, d_bact, w.ab.vals[0], w.act_r1);
+        RET(bwt_active_rounds(ctx, n, m, &k, w, &rounds, &passes_total));
+    }
+    LAUNCH(ctx, bwt_gather_kernel, grid_for((n + 3) / 4, 256), 256, 0, d_text, d_sa, n, d_last);
+    u32 *h_primary = (u32 *)(ctx->mailbox + 1040);
+    CU(ctx, cudaMemcpyAsync(h_primary, d_rank, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    CU(ctx, cudaGetLastError());
+    *primary = *h_primary;
+    ctx->stats.bwt_rounds = rounds;
+    ctx->stats.bwt_sort_passes = passes_total;
     return BZAP_OK;
 }

@@ -124,6 +124,7 @@ int dev_sort_positions_by_byte(bzap_ctx *ctx, const u8 *d_bytes, u32 n, u32 *d_T
 size_t sort_scratch_bytes(u32 n);
 // building blocks of the distributed single-block path
 int dev_init_keys(bzap_ctx *ctx, const u8 *d_text, u32 n, u32 lo, u32 m, u64 *d_keys);
+int dev_bwt_finish(bzap_ctx *ctx, const u8 *d_text, u32 n, u32 *d_sa, u32 *d_rank, u32 *d_rs, u64 k, u8 *d_last, u64 *primary);
 int dev_rerank_run(bzap_ctx *ctx, const u64 *d_keys, u32 m, u32 pos_base, u32 *d_rs, u32 counts[2]);
 int dev_sort_pairs_generic(bzap_ctx *ctx, u64 *d_keys, u32 *d_vals, u32 m, u64 *d_keys_tmp, u32 *d_vals_tmp,
                            int *result_in_tmp);

@@ -61,11 +61,11 @@ class GpuBackend:
         m = keys_sorted.numel()
         rs = torch.empty(m, dtype=torch.int32, device=self.device)
         if m == 0:
-            return rs, 0
+            return rs, 0, 0
         counts = (C.c_uint32 * 2)()
         _check(lib().bzap_dev_rerank(self.ctx.h, C.c_void_p(keys_sorted.data_ptr()), m, pos_base, C.c_void_p(rs.data_ptr()), counts),
                self.ctx.h)
-        return rs, int(counts[0])
+        return rs, int(counts[0]), int(counts[1])
 
     def partition_dest(self, keys, vals, split_keys, split_vals):
         m = keys.numel()
@@ -120,6 +120,16 @@ class GpuBackend:
                                               C.c_void_p(last.data_ptr())), self.ctx.h)
         return last
 
+    def finish_bwt(self, text, sa, rank, rs, k):
+        """Active rounds to the end on this GPU (bzap_dev_bwt_finish): returns (last column, primary)."""
+        n = text.numel()
+        last = torch.empty(n, dtype=torch.uint8, device=self.device)
+        prim = C.c_uint64(0)
+        _check(lib().bzap_dev_bwt_finish(self.ctx.h, C.c_void_p(text.data_ptr()), n, C.c_void_p(sa.data_ptr()),
+                                         C.c_void_p(rank.data_ptr()), C.c_void_p(rs.data_ptr()), k, C.c_void_p(last.data_ptr()),
+                                         C.byref(prim)), self.ctx.h)
+        return last, int(prim.value)
+
     def finish(self, last, n, primary):
         """MTF + Huffman + container on this GPU: the stages after bwt() (main.cpp:309-324)."""
         cap = lib().bzap_compress_bound(n)
@@ -144,6 +154,8 @@ def _install_signatures():
     L.bzap_dev_gather_last.argtypes = [vp, vp, sz, vp, sz, vp]
     L.bzap_dev_bucket_by_index.argtypes = [vp, vp, vp, sz, C.c_int, vp, vp, C.POINTER(C.c_uint32)]
     L.bzap_dev_bucket_by_index.restype = C.c_int
+    L.bzap_dev_bwt_finish.argtypes = [vp, vp, sz, vp, vp, vp, C.c_uint64, vp, C.POINTER(C.c_uint64)]
+    L.bzap_dev_bwt_finish.restype = C.c_int
     for f in ("bzap_dev_permute_pairs", "bzap_dev_scatter_u32", "bzap_dev_gather_last","bzap_dev_init_keys", "bzap_dev_sort_pairs", "bzap_dev_rerank", "bzap_dev_partition_dest",
               "bzap_dev_stable_perm_by_byte", "bzap_compress_from_bwt_device"):
         getattr(L, f).restype = C.c_int
@@ -296,11 +308,12 @@ def _rerank(keys_s, backend, group):
     dist.all_gather(allc, cnt, group=group)
     counts = [int(c) for c in torch.cat(allc).cpu()]
     pos_base = sum(counts[:me])
-    rs, heads = backend.rerank(keys_s, pos_base)
-    info = torch.zeros(4, dtype=torch.int64, device=dev)
+    rs, heads, singles = backend.rerank(keys_s, pos_base)
+    info = torch.zeros(5, dtype=torch.int64, device=dev)
     if m:
         info[0], info[1], info[2] = keys_s[0], keys_s[-1], rs[-1].long()
     info[3] = heads
+    info[4] = singles
     alli = [torch.empty_like(info) for _ in range(world)]
     dist.all_gather(alli, info, group=group)
     alli = torch.stack(alli).cpu().numpy()
@@ -308,10 +321,11 @@ def _rerank(keys_s, backend, group):
     bases = np.concatenate([[0], np.cumsum(counts)])
     prev_key, prev_val, have_prev = 0, 0, False
     carry_me, groups = None, 0
+    settled = int(alli[:, 4].sum())          # singleton groups, counted per rank (a seam can only lower it)
     for r in range(world):
         if counts[r] == 0:
             continue
-        first_key, last_key, last_rs, h = (int(x) for x in alli[r])
+        first_key, last_key, last_rs, h = (int(x) for x in alli[r][:4])
         cont = have_prev and first_key == prev_key
         groups += h - (1 if cont else 0)
         carry = prev_val if cont else None
@@ -323,7 +337,11 @@ def _rerank(keys_s, backend, group):
     if carry_me is not None and m:
         first_len = int(torch.searchsorted(rs, torch.tensor([pos_base], dtype=rs.dtype, device=dev), right=True))
         rs[:first_len] = carry_me
-    return rs, pos_base, groups
+    return rs, pos_base, groups, settled
+
+
+HANDOVER_DIVISOR = 2      # hand the block over to one GPU once at most half of the rotations are unsettled
+                          # (the same switch point as the single-GPU path, csrc/bwt.cu)
 
 
 def distributed_bwt(text, group=None, backend=None):
@@ -346,7 +364,7 @@ def distributed_bwt(text, group=None, backend=None):
     while True:
         keys_s, idx_s = _dist_sort(keys, idx.clone(), backend, group)
         t = _tick("", 0, dev) if _TIMING else 0.0
-        rs, pos_base, groups = _rerank(keys_s, backend, group)
+        rs, pos_base, groups, settled = _rerank(keys_s, backend, group)
         t = _tick("rerank", t, dev)
         rounds += 1
         # ranks go home: (index, rank) to the owner of the index.  One stable bucketing pass by the
@@ -367,6 +385,19 @@ def distributed_bwt(text, group=None, backend=None):
         if groups == n or k >= n or groups == prev_groups:
             break
         prev_groups = groups
+        if world > 1 and n - settled <= n // HANDOVER_DIVISOR:
+            # few rotations are still unsettled: further rounds would move all N pairs through the
+            # sample sort for nothing.  Rank 0 collects the suffix array, the ranks in both orders
+            # and finishes with the single-GPU active-set rounds (bzap_dev_bwt_finish).
+            (sa_full, rs_full), _ = _all_to_all([idx_s, rs], [idx_s.numel()] + [0] * (world - 1), group)
+            (rank_full,), _ = _all_to_all([rank_local], [m] + [0] * (world - 1), group)
+            prim = torch.zeros(1, dtype=torch.int64, device=dev)
+            last = None
+            if me == 0:
+                last, p0 = backend.finish_bwt(text, sa_full, rank_full, rs_full, k)
+                prim[0] = p0
+            dist.broadcast(prim, src=dist.get_global_rank(group, 0), group=group)
+            return last, int(prim[0]), rounds
         r2 = _fetch_shifted(rank_local, n, k, group) if world > 1 else torch.roll(rank_local, -(k % n))
         keys = (rank_local.long() << 32) | r2.long()
         k *= 2

@@ -158,6 +158,10 @@ int bzap_dev_permute_pairs(bzap_ctx *ctx, const uint64_t *d_keys, const uint32_t
 /* out[idx[j] - idx_offset] = vals[j]  (ranks written back into the owner's shard)                      */
 int bzap_dev_scatter_u32(bzap_ctx *ctx, const uint32_t *d_idx, const uint32_t *d_vals, size_t m, uint32_t idx_offset,
                          uint32_t *d_out);
+/* finishes a block whose first doubling rounds ran elsewhere: suffix array so far, ranks in text order
+ * and in suffix-array order (clobbered), all for prefix length k -> last column + primary index      */
+int bzap_dev_bwt_finish(bzap_ctx *ctx, const uint8_t *d_text, size_t n, uint32_t *d_sa, uint32_t *d_rank, uint32_t *d_rs,
+                        uint64_t k, uint8_t *d_last, uint64_t *primary);
 /* stable regroup of (index, value) pairs by digit (index >> shift) & 255; counts[256] on the host       */
 int bzap_dev_bucket_by_index(bzap_ctx *ctx, const uint32_t *d_idx, const uint32_t *d_vals, size_t m, int shift,
                              uint32_t *d_idx_out, uint32_t *d_vals_out, uint32_t counts[256]);

@@ -38,11 +38,34 @@ class NumpyBackend:
         k = keys_sorted.numpy()
         m = k.size
         if m == 0:
-            return torch.zeros(0, dtype=torch.int32), 0
+            return torch.zeros(0, dtype=torch.int32), 0, 0
         head = np.ones(m, dtype=bool)
         head[1:] = k[1:] != k[:-1]
         rs = pos_base + np.maximum.accumulate(np.where(head, np.arange(m), 0))
-        return torch.from_numpy(rs.astype(np.int32)), int(head.sum())
+        single = head & np.append(head[1:], True)
+        return torch.from_numpy(rs.astype(np.int32)), int(head.sum()), int(single.sum())
+
+    def finish_bwt(self, text, sa, rank, rs, k):
+        # stand-in for bzap_dev_bwt_finish: keep doubling (full sorts) on the gathered arrays
+        t = text.numpy()
+        n = t.size
+        rk = rank.numpy().astype(np.int64)
+        order = sa.numpy().astype(np.int64)
+        while k < n:
+            key = rk * (n + 1) + np.roll(rk, -(k % n))
+            order = np.argsort(key, kind="stable")
+            ks = key[order]
+            head = np.ones(n, dtype=bool)
+            head[1:] = ks[1:] != ks[:-1]
+            new = np.maximum.accumulate(np.where(head, np.arange(n), 0))
+            groups_before = np.unique(rk).size
+            rk = np.empty(n, dtype=np.int64)
+            rk[order] = new
+            k *= 2
+            if head.all() or np.unique(rk).size == groups_before:
+                break
+        last = t[(order + n - 1) % n]
+        return torch.from_numpy(last.copy()), int(rk[0])
 
     def partition_dest(self, keys, vals, sk, sv):
         k = keys.numpy().view(np.uint64)
