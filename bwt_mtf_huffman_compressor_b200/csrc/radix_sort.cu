@@ -21,29 +21,11 @@
 #ifndef RS_MINBLOCKS
 #define RS_MINBLOCKS 3
 #endif
-#ifndef RS_EARLY_VALS
-#define RS_EARLY_VALS 0
-#endif
-#ifndef RS_LATE_LOOKBACK
-#define RS_LATE_LOOKBACK 1
-#endif
 #ifndef RS_LB_WIDE
 #define RS_LB_WIDE 4
 #endif
-#ifndef RS_TWO_CHAINS
-#define RS_TWO_CHAINS 0
-#endif
 #ifndef RS_SMALL_N
 #define RS_SMALL_N (1u << 19)
-#endif
-#ifndef SC_VARIANT
-#define SC_VARIANT 1
-#endif
-#ifndef RS_ASYNC_VALS
-#define RS_ASYNC_VALS 0
-#endif
-#ifndef RS_BROADCAST_RANK
-#define RS_BROADCAST_RANK 0
 #endif
 #define RS_WARPS (RS_BLOCK / 32)
 #define RS_FLAG_AGG (1u << 30)
@@ -54,15 +36,9 @@ template <typename KeyT, int ITEMS> struct RsSmem {
     KeyT keys[RS_BLOCK * ITEMS];
     u32 vals[RS_BLOCK * ITEMS];
     u32 whist[RS_WARPS][256];
-#if RS_TWO_CHAINS
-    u32 whist2[RS_WARPS][256];         // counters of the second half of each thread's items
-#endif
     u32 adj[256];
     u32 scan_tmp[40];
     u32 ticket;
-#if RS_ASYNC_VALS
-    u32 vstage[RS_BLOCK * ITEMS];      // payloads land here by cp.async while the keys are ranked
-#endif
 };
 
 template <typename KeyT> __device__ __forceinline__ u32 digit_of(KeyT k, int shift)
@@ -99,54 +75,11 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
             key[j] = idx < n ? keys_in[idx] : (KeyT)~(KeyT)0;
         }
     }
-#if RS_ASYNC_VALS
-    // payloads: asynchronous global->shared copies (LDGSTS), no registers held, consumed after the
-    // ranking, the digit scan and the key regroup
-    if (!IOTA_VALS) {
-#pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            u32 idx = wbase + j * 32u + lane;
-            if (full_tile || idx < n) {
-                u32 dst = (u32)__cvta_generic_to_shared(&S.vstage[warp * (32u * ITEMS) + j * 32u + lane]);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(vals_in + idx) : "memory");
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-#endif
     for (u32 i = lane; i < 256; i += 32) S.whist[warp][i] = 0;
     __syncwarp();
 
     // warp-level multisplit: rank of each key among the warp's keys with the same digit
     u32 *wh = S.whist[warp];
-#if RS_TWO_CHAINS
-    // The counter update makes consecutive items a dependent chain (match -> read -> write ->
-    // shuffle).  The items are ranked as two independent halves with their own counters, two chains
-    // in flight per warp, and the second half is shifted by the first half's counts afterwards.
-    u32 *wh2 = S.whist2[warp];
-    for (u32 i = lane; i < 256; i += 32) wh2[i] = 0;
-    __syncwarp();
-    constexpr int HALF = ITEMS / 2;
-#pragma unroll
-    for (int j = 0; j < HALF; ++j) {
-        u32 da = digit_of(key[j], shift), db = digit_of(key[j + HALF], shift);
-        u32 ma = __match_any_sync(FULL_MASK, da), mb = __match_any_sync(FULL_MASK, db);
-        u32 la = (u32)__ffs(ma) - 1u, lb = (u32)__ffs(mb) - 1u;
-        u32 pa = 0, pb = 0;
-        if (lane == la) { pa = wh[da]; wh[da] = pa + (u32)__popc(ma); }
-        if (lane == lb) { pb = wh2[db]; wh2[db] = pb + (u32)__popc(mb); }
-        pa = __shfl_sync(FULL_MASK, pa, la);
-        pb = __shfl_sync(FULL_MASK, pb, lb);
-        rnk[j] = pa + (u32)__popc(ma & lanemask_lt());
-        rnk[j + HALF] = pb + (u32)__popc(mb & lanemask_lt());
-        __syncwarp();
-    }
-#pragma unroll
-    for (int j = HALF; j < 2 * HALF; ++j) rnk[j] += wh[digit_of(key[j], shift)];
-    __syncwarp();
-    for (u32 i = lane; i < 256; i += 32) wh[i] += wh2[i];
-    static_assert(ITEMS % 2 == 0, "two ranking chains need an even item count");
-#else
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         u32 d = digit_of(key[j], shift);
@@ -161,7 +94,6 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
         rnk[j] = prev + (u32)__popc(m & lanemask_lt());
         __syncwarp();
     }
-#endif
     __syncthreads();
 
     // thread b owns digit b: prefix over warps, publish the tile's count, scan over digits
@@ -190,7 +122,7 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
         }
     }
     // global base of digit `bin`: decoupled look-back over the previous tiles.  It only feeds the
-    // final write-out, so (RS_LATE_LOOKBACK) it runs after the shared-memory regroup, which gives
+    // final write-out, so it runs after the shared-memory regroup, which gives
     // the predecessors time to publish their inclusive prefixes; status words are fetched
     // RS_LB_WIDE at a time so that a deep walk is not a chain of dependent L2 round trips.
     auto look_back = [&]() {
@@ -219,36 +151,15 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
         }
         S.adj[bin] = offsets[bin] + excl - tile_start;
     };
-#if !RS_LATE_LOOKBACK
-    look_back();
-#endif
     __syncthreads();
 
     // regroup keys and payloads by digit in shared memory
-#if RS_EARLY_VALS
-    u32 val[ITEMS];
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-        u32 idx = wbase + j * 32u + lane;
-        if (IOTA_VALS) val[j] = idx;
-        else val[j] = (full_tile || idx < n) ? vals_in[idx] : 0u;
-    }
-#endif
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) {
         u32 pos = wh[digit_of(key[j], shift)] + rnk[j];
         S.keys[pos] = key[j];
         rnk[j] = pos;
     }
-#if RS_ASYNC_VALS
-    u32 val[ITEMS];
-    if (!IOTA_VALS) asm volatile("cp.async.wait_group 0;" ::: "memory");
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-        if (IOTA_VALS) val[j] = wbase + j * 32u + lane;
-        else val[j] = S.vstage[warp * (32u * ITEMS) + j * 32u + lane];     // this thread's own copies
-    }
-#elif !RS_EARLY_VALS
     // payload loads are issued only now: the key registers are dead
     u32 val[ITEMS];
 #pragma unroll
@@ -257,12 +168,9 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
         if (IOTA_VALS) val[j] = idx;
         else val[j] = (full_tile || idx < n) ? vals_in[idx] : 0u;
     }
-#endif
 #pragma unroll
     for (int j = 0; j < ITEMS; ++j) S.vals[rnk[j]] = val[j];
-#if RS_LATE_LOOKBACK
     look_back();
-#endif
     __syncthreads();
 
     // contiguous per-digit runs go out; padding keys (digit 255, highest tile index) sit last
@@ -469,19 +377,8 @@ __global__ void perm_offsets_kernel(u32 n, int shift, u32 *offsets)
 __global__ void __launch_bounds__(256)
 scatter_u32_kernel(const u32 *__restrict__ idx, const u32 *__restrict__ vals, u32 n, u32 *__restrict__ out)
 {
-#if SC_VARIANT == 0
-    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) out[idx[j]] = vals[j];
-#elif SC_VARIANT == 1
-    // streaming loads: the inputs are read once and must not push the half-written target sectors out of L2
+    // streaming loads: the inputs are read once and must not push half-written target sectors out of L2
     for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) out[__ldcs(idx + j)] = __ldcs(vals + j);
-#elif SC_VARIANT == 2
-    // contiguous chunk per block: a block stays inside one target window for its whole life
-    const u32 per = (n + gridDim.x - 1) / gridDim.x;
-    const u32 lo = blockIdx.x * per, hi = min(n, lo + per);
-    for (u32 j = lo + threadIdx.x; j < hi; j += blockDim.x) out[__ldcs(idx + j)] = __ldcs(vals + j);
-#elif SC_VARIANT == 3
-    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) __stwt(out + __ldcs(idx + j), __ldcs(vals + j));
-#endif
 }
 
 int dev_scatter_perm(bzap_ctx *ctx, const u32 *d_perm, const u32 *d_vals, u32 n, u32 *d_out, u32 *d_tmp_idx,
