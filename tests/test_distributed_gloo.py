@@ -45,8 +45,12 @@ class NumpyBackend:
         single = head & np.append(head[1:], True)
         return torch.from_numpy(rs.astype(np.int32)), int(head.sum()), int(single.sum())
 
+    handovers = 0
+
     def finish_bwt(self, text, sa, rank, rs, k):
         # stand-in for bzap_dev_bwt_finish: keep doubling (full sorts) on the gathered arrays
+        NumpyBackend.handovers += 1
+        assert np.array_equal(rank.numpy()[sa.numpy()], rs.numpy())      # the three arrays agree
         t = text.numpy()
         n = t.size
         rk = rank.numpy().astype(np.int64)
@@ -112,6 +116,13 @@ def test_shift_plan_covers_every_range_exactly_once():
             assert sorted(got) == want
 
 
+def _with_repeats(rng):
+    d = rng.integers(0, 256, 9000, dtype=np.uint8)
+    d[4000:4300] = d[1000:1300]
+    d[7000:7300] = d[1000:1300]
+    return d
+
+
 def _cases():
     rng = np.random.default_rng(3)
     return {
@@ -123,6 +134,8 @@ def _cases():
         "a_then_b": np.concatenate([np.full(1500, 97, dtype=np.uint8), [98]]).astype(np.uint8),
         "tiny": np.frombuffer(b"banana", dtype=np.uint8).copy(),
         "text": np.frombuffer((b"the quick brown fox jumps over the lazy dog " * 60), dtype=np.uint8).copy(),
+        # mostly settled after two rounds, a few long repeats left: the hand-over to one rank is taken
+        "handover": _with_repeats(rng),
     }
 
 
@@ -133,6 +146,7 @@ def _worker(rank, world, port, q):
     for name, d in _cases().items():
         last, primary, rounds = D.distributed_bwt(torch.from_numpy(d.copy()), None, NumpyBackend())
         out[name] = (None if last is None else last.numpy().tobytes(), primary, rounds)
+    out["__handovers__"] = NumpyBackend.handovers
     dist.barrier()
     q.put((rank, out))
     dist.destroy_process_group()
@@ -154,6 +168,8 @@ def test_distributed_bwt_matches_oracle_over_gloo(world):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    assert res[0]["__handovers__"] >= 1            # the hand-over path ran on rank 0 ...
+    assert all(res[r]["__handovers__"] == 0 for r in range(1, world))     # ... and only there
     for name, d in _cases().items():
         ol, op = O.o_bwt(d)
         last, primary, rounds = res[0][name]
