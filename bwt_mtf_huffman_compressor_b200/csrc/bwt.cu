@@ -60,12 +60,6 @@ bwt_init_keys_kernel(const u8 *__restrict__ text, u32 n, u32 lo, u32 m, u64 *__r
     }
 }
 
-// hist8[p][d] = src[(p % src_rows)][d] : every pass digit shares the same few histograms
-__global__ void bwt_spread_hist_kernel(const u32 *__restrict__ src, int src_rows, u32 *__restrict__ hist8)
-{
-    for (int p = 0; p < 8; ++p) hist8[p * 256 + threadIdx.x] = src[(p % src_rows) * 256 + threadIdx.x];
-}
-
 // ---- doubling keys (full rounds) -----------------------------------------------------------------
 __global__ void __launch_bounds__(256) bwt_pair_keys_kernel(const u32 *__restrict__ rank, u32 n, u32 k, u64 *__restrict__ keys)
 {
@@ -491,6 +485,8 @@ struct ActiveWork {
     u64 *d_status, *cstatus;
     size_t arena_mark;
     u32 rank_mask;
+    u8 *zero_base;                        // hist8, rrctl and cstatus are allocated back to back:
+    size_t zero_bytes;                    // one memset per round clears all three
 };
 
 // w.ab.vals[0] / w.act_r1 hold the m unsettled rotations (start, group rank) in suffix-array order;
@@ -500,22 +496,21 @@ static int bwt_active_rounds(bzap_ctx *ctx, u32 n, u32 m, u64 *k_io, const Activ
     u64 k = *k_io;
     u32 *h_cnt = (u32 *)(ctx->mailbox + 1024);
     SortBuffers ab = w.ab;
+    u32 *act_r1 = w.act_r1, *next_idx = w.next_idx, *next_r1 = w.next_r1;
     while (m) {
         const u32 mt = (m + AC_TILE - 1) / AC_TILE;
-        CU(ctx, cudaMemsetAsync(w.d_hist8, 0, 8 * 256 * sizeof(u32), ctx->stream));
-        LAUNCH(ctx, bwt_active_keys_kernel, grid_for(m, 256, 148 * 4), 256, 0, ab.vals[0], w.act_r1, m, w.d_rank, n,
+        CU(ctx, cudaMemsetAsync(w.zero_base, 0, w.zero_bytes, ctx->stream));
+        LAUNCH(ctx, bwt_active_keys_kernel, grid_for(m, 256, 148 * 4), 256, 0, ab.vals[0], act_r1, m, w.d_rank, n,
                (u32)(k % n), ab.keys[0], w.d_hist8);
         int passes = 0;
         u64 *skeys = nullptr;
         u32 *sidx = nullptr;
         ctx->arena_off = w.arena_mark;
-        RET(dev_sort_pairs64(ctx, &ab, m, w.rank_mask, w.d_hist8, false, &skeys, &sidx, &passes));
+        RET(dev_sort_pairs64(ctx, &ab, m, w.rank_mask, w.d_hist8, 8, false, &skeys, &sidx, &passes));
         *passes_total += (u32)passes;
-        CU(ctx, cudaMemsetAsync(w.d_rrctl, 0, w.rrctl_bytes, ctx->stream));
         LAUNCH(ctx, bwt_active_rerank_kernel, mt, AC_BLOCK, 0, skeys, sidx, m, w.sa_buf, w.d_rank, w.newr, w.pos, w.d_counters,
                w.d_status, w.d_status + mt + 2, w.d_ticket);
-        CU(ctx, cudaMemsetAsync(w.cstatus, 0, ((size_t)mt + 2) * sizeof(u64), ctx->stream));
-        LAUNCH(ctx, bwt_active_compact_kernel, mt, AC_BLOCK, 0, w.newr, w.pos, sidx, m, w.next_idx, w.next_r1, w.d_counters + 2,
+        LAUNCH(ctx, bwt_active_compact_kernel, mt, AC_BLOCK, 0, w.newr, w.pos, sidx, m, next_idx, next_r1, w.d_counters + 2,
                w.cstatus, w.d_ticket + 1);
         CU(ctx, cudaMemcpyAsync(h_cnt, w.d_counters, 3 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -523,9 +518,17 @@ static int bwt_active_rounds(bzap_ctx *ctx, u32 n, u32 m, u64 *k_io, const Activ
         k *= 2;
         const u32 groups = h_cnt[0], subgroups = h_cnt[1], m2 = h_cnt[2];
         if (m2 == 0 || k >= n || subgroups == groups) break;
-        // survivors become the next round's input (copy into the sort's payload buffer 0)
-        CU(ctx, cudaMemcpyAsync(ab.vals[0], w.next_idx, (size_t)m2 * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
-        CU(ctx, cudaMemcpyAsync(w.act_r1, w.next_r1, (size_t)m2 * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+        // survivors become the next round's input: swap buffers instead of copying.  The sorted
+        // payload may sit in either ab.vals[]; the one it does NOT sit in is free to become the
+        // next survivor buffer, and the survivor buffer becomes the sort's payload buffer 0.
+        {
+            u32 *free_vals = sidx == ab.vals[0] ? ab.vals[1] : ab.vals[0];
+            u32 *used_vals = sidx;
+            ab.vals[0] = next_idx;
+            ab.vals[1] = free_vals;
+            next_idx = used_vals;
+            u32 *t = act_r1; act_r1 = next_r1; next_r1 = t;
+        }
         m = m2;
     }
     *k_io = k;
@@ -597,7 +600,6 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
     // round 0: byte histogram stands in for all eight digit histograms of the 8-byte windows
     CU(ctx, cudaMemsetAsync(d_hist4, 0, 256 * sizeof(u32), ctx->stream));
     RET(dev_byte_hist(ctx, d_in, n, d_hist4));
-    LAUNCH(ctx, bwt_spread_hist_kernel, 1, 256, 0, d_hist4, 1, d_hist8);
     LAUNCH(ctx, bwt_init_keys_kernel, grid_for((n + IK_TILE - 1) / IK_TILE, 1, 148 * 8), IK_BLOCK, 0, d_in, n, 0u, n, sb.keys[0]);
 
     // digits of (rank << 32 | rank) that can differ at all: ranks are < n
@@ -616,7 +618,8 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
     while (true) {
         int passes = 0;
         ctx->arena_off = arena_mark;             // sort control block is per round
-        RET(dev_sort_pairs64(ctx, &sb, n, rounds == 0 ? 0xffu : rank_mask, d_hist8, true, &keys, &sa, &passes));
+        // round 0: one byte histogram serves all eight digits; later: four rank-digit histograms serve both key halves
+        RET(dev_sort_pairs64(ctx, &sb, n, rounds == 0 ? 0xffu : rank_mask, d_hist4, rounds == 0 ? 1 : 4, true, &keys, &sa, &passes));
         passes_total += (u32)passes;
         CU(ctx, cudaMemsetAsync(d_rrctl, 0, rrctl_bytes, ctx->stream));
         // rank[] is larger than L2 for big blocks: scatter it through a bucketing pass (radix_sort.cu)
@@ -632,7 +635,6 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
         if (groups == n || k >= n || groups == prev_groups) { finished = true; break; }
         prev_groups = groups;
         if (active <= n / 2) break;              // few rotations left unsettled: switch regime
-        LAUNCH(ctx, bwt_spread_hist_kernel, 1, 256, 0, d_hist4, 4, d_hist8);
         // keys always rebuilt into buffer 0 in text order; payload = identity again
         LAUNCH(ctx, bwt_pair_keys_kernel, grid_for(n, 256 * 4), 256, 0, d_rank, n, (u32)(k % n), sb.keys[0]);
         k *= 2;
@@ -665,6 +667,8 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
         w.sa_buf = sa_buf; w.d_rank = d_rank; w.d_hist8 = d_hist8; w.d_rrctl = d_rrctl; w.rrctl_bytes = rrctl_bytes;
         w.d_counters = d_counters; w.d_ticket = d_ticket; w.d_status = d_status; w.cstatus = cstatus;
         w.arena_mark = arena_mark; w.rank_mask = rank_mask;
+        w.zero_base = (u8 *)d_hist8;
+        w.zero_bytes = (size_t)((u8 *)(cstatus + ac_tiles_max + 4) - (u8 *)d_hist8);
         RET(bwt_active_rounds(ctx, n, active, &k, w, &rounds, &passes_total));
         sa = sa_buf;
     }
@@ -774,6 +778,8 @@ int dev_bwt_finish(bzap_ctx *ctx, const u8 *d_text, u32 n, u32 *d_sa, u32 *d_ran
         while (rank_bits < 32 && (1ull << rank_bits) < n) ++rank_bits;
         const u32 nd = (rank_bits + 7) / 8;
         w.rank_mask = ((1u << nd) - 1u) | (((1u << nd) - 1u) << 4);
+        w.zero_base = (u8 *)w.d_hist8;
+        w.zero_bytes = (size_t)((u8 *)(w.cstatus + mt + 4) - (u8 *)w.d_hist8);
         LAUNCH(ctx, bwt_collect_active_kernel, rr_grid, RR_BLOCK, 0, d_rs, d_sa, n, rr_tiles, d_bact, w.ab.vals[0], w.act_r1);
         RET(bwt_active_rounds(ctx, n, m, &k, w, &rounds, &passes_total));
     }

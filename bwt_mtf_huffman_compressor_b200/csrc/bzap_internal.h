@@ -116,7 +116,7 @@ struct SortBuffers {
     u64 *keys[2];
     u32 *vals[2];
 };
-int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, u32 pass_mask, u32 *d_hist, bool vals_are_iota,
+int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, u32 pass_mask, const u32 *d_hist, int hist_rows, bool vals_are_iota,
                      u64 **out_keys, u32 **out_vals, int *passes_run);
 // stable counting sort of positions by byte value: T[r] = position of the r-th smallest (byte, pos)
 // (main.cpp:67); d_cum receives the 257 exclusive byte counts

@@ -187,14 +187,15 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
 }
 
 // ---- digit offsets -------------------------------------------------------------------------------
-// hist: passes x 256 counts.  offsets: passes x 256 exclusive sums.  trivial[p] = 1 when one digit
+// hist: hist_rows x 256 counts, pass p uses row p % hist_rows (several digits often share one
+// histogram, see bwt.cu).  offsets: passes x 256 exclusive sums.  trivial[p] = 1 when one digit
 // value holds all n keys (the pass is the identity permutation).
-__global__ void radix_offsets_kernel(const u32 *__restrict__ hist, u32 *__restrict__ offsets, u32 *trivial, u32 n,
-                                     int passes)
+__global__ void radix_offsets_kernel(const u32 *__restrict__ hist, int hist_rows, u32 *__restrict__ offsets, u32 *trivial,
+                                     u32 n, int passes)
 {
     __shared__ u32 s_tmp[40];
     for (int p = 0; p < passes; ++p) {
-        u32 c = hist[p * 256 + threadIdx.x];
+        u32 c = hist[(p % hist_rows) * 256 + threadIdx.x];
         u32 total;
         u32 ex = block_exclusive_sum(c, s_tmp, &total);
         offsets[p * 256 + threadIdx.x] = ex;
@@ -261,7 +262,8 @@ template <typename K> static int set_smem_attr(bzap_ctx *ctx, K kernel, size_t b
     return BZAP_OK;
 }
 
-int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, u32 pass_mask, u32 *d_hist, bool vals_are_iota, u64 **out_keys,
+int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, u32 pass_mask, const u32 *d_hist, int hist_rows, bool vals_are_iota,
+                     u64 **out_keys,
                      u32 **out_vals, int *passes_run)
 {
     constexpr int ITEMS = RS_ITEMS_64;
@@ -273,7 +275,7 @@ int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, u32 pass_mask, u32 *d
     if (!d_ctl) return bzap_fail(ctx, BZAP_ERR_NOMEM, "sort scratch");
     u32 *d_offsets = d_ctl, *d_trivial = d_ctl + 8 * 256, *d_ticket = d_trivial + 8, *d_status = d_ticket + 8;
     CU(ctx, cudaMemsetAsync(d_trivial, 0, (16 + passes * status_words) * sizeof(u32), ctx->stream));
-    LAUNCH(ctx, radix_offsets_kernel, 1, 256, 0, d_hist, d_offsets, d_trivial, n, passes);
+    LAUNCH(ctx, radix_offsets_kernel, 1, 256, 0, d_hist, hist_rows, d_offsets, d_trivial, n, passes);
     u32 *h_trivial = (u32 *)ctx->mailbox;
     if (n <= RS_SMALL_N) {
         // small inputs are launch / sync latency bound: a host round trip to learn which passes are
@@ -440,7 +442,7 @@ int dev_sort_pairs_generic(bzap_ctx *ctx, u64 *d_keys, u32 *d_vals, u32 m, u64 *
     u64 *ok = nullptr;
     u32 *ov = nullptr;
     int passes = 0;
-    RET(dev_sort_pairs64(ctx, &sb, m, 0xffu, d_hist8, false, &ok, &ov, &passes));
+    RET(dev_sort_pairs64(ctx, &sb, m, 0xffu, d_hist8, 8, false, &ok, &ov, &passes));
     *result_in_tmp = ok == d_keys_tmp;
     return BZAP_OK;
 }
