@@ -260,3 +260,22 @@ def test_payload_shorter_than_header_claims():
     with pytest.raises(bz.BzapError) as e:
         bz.decompress_bytes(cut)
     assert e.value.code == bz.ERR_CORRUPT
+
+
+def test_text_256m_roundtrip_property():
+    # beyond the goldens: a 256 MiB block (4x BASELINE config 3) must round-trip bit-exactly, and
+    # header / sizes must be self-consistent (the reference would need ~4 minutes for this file)
+    import torch
+    n = 1 << 28
+    d = W.synthetic_text(n, 0x5EED0256)
+    ctx = bz.Context()
+    x = torch.from_numpy(d).cuda()
+    out = torch.empty(bz.compress_bound(n), dtype=torch.uint8, device="cuda")
+    fl = ctx.compress_ptr(x.data_ptr(), n, out.data_ptr(), out.numel(), device=True)
+    head = out[:24].cpu().numpy()
+    primary, nn, tb = (int(v) for v in np.frombuffer(head.tobytes(), dtype="<u8"))
+    assert nn == n and primary < n and 2 <= tb <= 320 and fl > 24 + tb
+    back = torch.empty(n, dtype=torch.uint8, device="cuda")
+    m = ctx.decompress_ptr(out.data_ptr(), fl, back.data_ptr(), n, device=True)
+    assert m == n and bool(torch.equal(back, x))
+    ctx.close()
