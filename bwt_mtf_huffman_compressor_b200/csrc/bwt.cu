@@ -74,9 +74,9 @@ __global__ void __launch_bounds__(256) bwt_pair_keys_kernel(const u32 *__restric
 // ---- re-rank (full rounds) ---------------------------------------------------------------------------
 // sorted keys (+ payload = rotation start, nullptr = identity) -> rank[start] = sparse rank (text
 // order), rs[j] = the same rank in sorted order, number of groups, number of singleton groups, and
-// the 4 x 256 histogram of rank digits for the next round's passes.  Persistent blocks take tiles
-// by ticket so that the shared-memory histogram is flushed once per block, not once per tile.
-// blocked accesses (thread t owns elements 8t..8t+7) would put 16 lanes on one bank pair: one pad
+// the 4 x 256 histogram of rank digits for the next round's passes.  A few hundred blocks each walk
+// a contiguous range of tiles, so the shared-memory histogram is flushed once per block.
+// Blocked accesses (thread t owns elements 8t..8t+7) would put 16 lanes on one bank pair: one pad
 // slot per 8 elements makes the lane stride 9 (conflict free for 32- and 64-bit words)
 #define RR_PAD(x) ((x) + ((x) >> 3))
 struct RrSmem {
