@@ -700,7 +700,7 @@ int dev_rerank_run(bzap_ctx *ctx, const u64 *d_keys, u32 m, u32 pos_base, u32 *d
     u32 *d_ctl = arena_get<u32>(ctx, words);
     if (!d_ctl) return bzap_fail(ctx, BZAP_ERR_NOMEM, "rerank scratch");
     CU(ctx, cudaMemsetAsync(d_ctl, 0, words * sizeof(u32), ctx->stream));
-    u32 *d_hist4 = d_ctl, *d_counters = d_ctl + 4 * 256, *d_ticket = d_counters + 4;
+    u32 *d_hist4 = d_ctl, *d_counters = d_ctl + 4 * 256;
     u64 *d_status = (u64 *)(d_ctl + 4 * 256 + 8);
     LAUNCH(ctx, bwt_rerank_kernel, grid_for(rr_tiles, 1, 148 * 6), RR_BLOCK, 0, d_keys, (const u32 *)nullptr, m, rr_tiles,
            pos_base, (u32 *)nullptr, d_rs, d_hist4, d_counters, d_status, (u32 *)nullptr);

@@ -2,16 +2,20 @@
 //
 // Replaces std::stable_sort in bwt() (main.cpp:82) and bwt_reverse() (main.cpp:67).  One pass =
 // ONE kernel that reads every (key, payload) once and writes it once:
-//   * digit counts for all passes are accumulated up front by the kernel that PRODUCES the keys
-//     (fused, bwt.cu) or by radix_hist_u8 below, then turned into global digit offsets;
+//   * digit counts for all passes are known before the first pass: they come from the kernel that
+//     PRODUCES the keys (bwt.cu: one byte histogram, or the rank-digit histogram fused into the
+//     re-rank kernel), from radix_hist_u8 below, or in closed form (permutation payloads);
 //   * each 256-thread block takes a tile by atomic ticket, ranks its keys with warp-level
-//     match-any multisplit into per-warp shared-memory digit counters, publishes the tile's 256
-//     digit counts and resolves its global base per digit by decoupled look-back over the
-//     previous tiles' status words (flag+count in one 32-bit word);
-//   * keys and payloads are regrouped by digit in shared memory and written out as contiguous
-//     per-digit runs.
-// Passes whose digit is constant over all keys are skipped on the host after reading back the
-// per-pass "trivial" flags; that is what makes periodic inputs (all keys equal) cheap.
+//     match-any multisplit into per-warp shared-memory digit counters and publishes the tile's 256
+//     digit counts (flag+count in one 32-bit status word);
+//   * keys and payloads are regrouped by digit in shared memory; only then is the tile's global
+//     base per digit resolved by decoupled look-back over the previous tiles' status words, four
+//     words per step, so that the wait overlaps the predecessors' own progress;
+//   * the regrouped tile goes out as contiguous per-digit runs.
+// Passes whose digit is constant over all keys are skipped: large sorts read the per-pass
+// "trivial" flags back (that is what makes periodic inputs, all keys equal, cheap), small sorts
+// take a host-computed mask of digits that can vary at all instead of a round trip.
+// Measured variants of this kernel: profiles/r1_onesweep_variants.md.
 #include "device_common.cuh"
 #include <cstring>
 
