@@ -21,7 +21,12 @@
 // (conflict free); a move-to-front is a byte-wise funnel shift over the first pos/4+1 words.
 #include "device_common.cuh"
 
+#ifndef MTF_THREADS
 #define MTF_THREADS 128          // threads (= chunks) per block in the per-chunk kernels
+#endif
+#ifndef MTF_TARGET_CHUNKS
+#define MTF_TARGET_CHUNKS (148u * 512u)
+#endif
 #define MTF_GROUP 128            // chunks per scan group
 
 __device__ __forceinline__ u32 low_bytes_mask(u32 r)   // low (r+1) bytes
@@ -312,7 +317,7 @@ imtf_apply_kernel(const u8 *__restrict__ in, u32 n, u32 chunk, u32 nchunks, cons
 // chunk length: multiple of 16, aims at >= ~64K chunks on big inputs and enough threads on small ones
 static u32 pick_chunk(u32 n)
 {
-    u32 target = 148u * 512u;
+    u32 target = MTF_TARGET_CHUNKS;
     u32 c = (n + target - 1) / target;
     c = (c + 15u) & ~15u;
     if (c < 128) c = 128;

@@ -25,10 +25,10 @@ for name, d in cases.items():
         s = ctx.stats()
         ctx.decompress_ptr(out.data_ptr(), fl, back.data_ptr(), n, device=True)
         sd = ctx.stats()
-        row = (s.ms_total, s.ms_bwt, s.ms_sort, s.bwt_full_passes, s.sort_bytes, s.bwt_rounds, s.bwt_sort_passes, sd.ms_total, sd.ms_bwt)
+        row = (s.ms_total, s.ms_bwt, s.ms_sort, s.bwt_full_passes, s.sort_bytes, s.bwt_rounds, s.bwt_sort_passes, sd.ms_total, sd.ms_bwt, s.ms_mtf, sd.ms_mtf)
         if best is None or row[0] < best[0]:
             best = row
     ok = bool(torch.equal(back, x))
     gbs = best[4] / (best[2] * 1e-3) / 1e9 if best[2] > 0 else 0
-    print("%-14s %-12s compress %.2f ms (bwt %.2f, full passes %d in %.2f ms = %.0f GB/s, rounds %d, passes %d) decompress %.2f ms (ibwt %.2f) roundtrip_ok=%s"
-          % (tag, name, best[0], best[1], best[3], best[2], gbs, best[5], best[6], best[7], best[8], ok), flush=True)
+    print("%-14s %-12s compress %.2f ms (bwt %.2f, full passes %d in %.2f ms = %.0f GB/s, rounds %d, passes %d) decompress %.2f ms (ibwt %.2f) mtf %.3f imtf %.3f roundtrip_ok=%s"
+          % (tag, name, best[0], best[1], best[3], best[2], gbs, best[5], best[6], best[7], best[8], best[9], best[10], ok), flush=True)
