@@ -600,7 +600,8 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
     // round 0: byte histogram stands in for all eight digit histograms of the 8-byte windows
     CU(ctx, cudaMemsetAsync(d_hist4, 0, 256 * sizeof(u32), ctx->stream));
     RET(dev_byte_hist(ctx, d_in, n, d_hist4));
-    LAUNCH(ctx, bwt_init_keys_kernel, grid_for((n + IK_TILE - 1) / IK_TILE, 1, 148 * 8), IK_BLOCK, 0, d_in, n, 0u, n, sb.keys[0]);
+    // the keys themselves are built inside the first sort pass of every round (SortKeyGen)
+    SortKeyGen gen{1, d_in, 0};
 
     // digits of (rank << 32 | rank) that can differ at all: ranks are < n
     u32 rank_bits = 1;
@@ -619,7 +620,16 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
         int passes = 0;
         ctx->arena_off = arena_mark;             // sort control block is per round
         // round 0: one byte histogram serves all eight digits; later: four rank-digit histograms serve both key halves
-        RET(dev_sort_pairs64(ctx, &sb, n, rounds == 0 ? 0xffu : rank_mask, d_hist4, rounds == 0 ? 1 : 4, true, &keys, &sa, &passes));
+        RET(dev_sort_pairs64(ctx, &sb, n, rounds == 0 ? 0xffu : rank_mask, d_hist4, rounds == 0 ? 1 : 4, true, &keys, &sa, &passes,
+                             &gen));
+        if (!keys) {
+            // every digit is constant (all keys equal): no pass ran, write the keys out for the re-rank
+            keys = sb.keys[0];
+            if (gen.mode == 1)
+                LAUNCH(ctx, bwt_init_keys_kernel, grid_for((n + IK_TILE - 1) / IK_TILE, 1, 148 * 8), IK_BLOCK, 0, d_in, n, 0u, n, keys);
+            else
+                LAUNCH(ctx, bwt_pair_keys_kernel, grid_for(n, 256 * 4), 256, 0, d_rank, n, gen.k, keys);
+        }
         passes_total += (u32)passes;
         CU(ctx, cudaMemsetAsync(d_rrctl, 0, rrctl_bytes, ctx->stream));
         // rank[] is larger than L2 for big blocks: scatter it through a bucketing pass (radix_sort.cu)
@@ -635,8 +645,8 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
         if (groups == n || k >= n || groups == prev_groups) { finished = true; break; }
         prev_groups = groups;
         if (active <= n / 2) break;              // few rotations left unsettled: switch regime
-        // keys always rebuilt into buffer 0 in text order; payload = identity again
-        LAUNCH(ctx, bwt_pair_keys_kernel, grid_for(n, 256 * 4), 256, 0, d_rank, n, (u32)(k % n), sb.keys[0]);
+        // next round's keys: (rank[i], rank[i + k]) in text order, payload = identity again
+        gen = SortKeyGen{2, d_rank, (u32)(k % n)};
         k *= 2;
     }
     // ---- active rounds ----

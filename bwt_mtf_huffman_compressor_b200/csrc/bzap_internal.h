@@ -116,8 +116,16 @@ struct SortBuffers {
     u64 *keys[2];
     u32 *vals[2];
 };
+// gen != nullptr (only with vals_are_iota): the keys are not in b->keys[0] yet; the first executed
+// pass builds them from gen->src (mode 1: 8-byte text windows, mode 2: rank pairs at distance k).
+// If no pass executes, *out_keys is nullptr and the caller materialises the keys itself.
+struct SortKeyGen {
+    int mode;
+    const void *src;
+    u32 k;
+};
 int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, u32 pass_mask, const u32 *d_hist, int hist_rows, bool vals_are_iota,
-                     u64 **out_keys, u32 **out_vals, int *passes_run);
+                     u64 **out_keys, u32 **out_vals, int *passes_run, const SortKeyGen *gen = nullptr);
 // stable counting sort of positions by byte value: T[r] = position of the r-th smallest (byte, pos)
 // (main.cpp:67); d_cum receives the 257 exclusive byte counts
 int dev_sort_positions_by_byte(bzap_ctx *ctx, const u8 *d_bytes, u32 n, u32 *d_T, u32 *d_cum);

@@ -51,11 +51,16 @@ template <typename KeyT> __device__ __forceinline__ u32 digit_of(KeyT k, int shi
 }
 
 // offsets = exclusive global digit offsets of this pass (256); status = tiles*256 zeroed words
-template <typename KeyT, int ITEMS, bool IOTA_VALS, bool WRITE_KEYS>
+//
+// KEYGEN: where the keys of this pass come from.  0 = keys_in.  The first pass of a BWT sort builds
+// its 64-bit keys on the fly instead of reading an array another kernel wrote (bwt.cu):
+// 1 = the 8-byte cyclic window of the text at each position (gen_src = text bytes, main.cpp:38-44),
+// 2 = (rank[i] << 32 | rank[(i + gen_k) % n]) (gen_src = ranks in text order).
+template <typename KeyT, int ITEMS, bool IOTA_VALS, bool WRITE_KEYS, int KEYGEN = 0>
 __global__ void __launch_bounds__(RS_BLOCK, RS_MINBLOCKS)
 onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out, const u32 *__restrict__ vals_in,
                      u32 *__restrict__ vals_out, u32 n, int shift, const u32 *__restrict__ offsets, u32 *status,
-                     u32 *ticket)
+                     u32 *ticket, const void *__restrict__ gen_src = nullptr, u32 gen_k = 0)
 {
     extern __shared__ __align__(16) u8 smem_raw[];
     RsSmem<KeyT, ITEMS> &S = *reinterpret_cast<RsSmem<KeyT, ITEMS> *>(smem_raw);
@@ -69,7 +74,48 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
     KeyT key[ITEMS];
     u32 rnk[ITEMS];
     const bool full_tile = valid == TILE;          // uniform: all but the last tile skip the bounds checks
-    if (full_tile) {
+    if (KEYGEN == 1) {
+        // stage the tile's bytes (+7 of the next tile, cyclic) in the payload array, which is idle until the regroup
+        u8 *sb = reinterpret_cast<u8 *>(S.vals);
+        const u8 *text = static_cast<const u8 *>(gen_src);
+        if ((u64)tile_base + TILE + 8 <= n && (reinterpret_cast<uintptr_t>(text) & 15u) == 0) {
+            // interior tile of an aligned text: one 16-byte load per thread (TILE = 16 bytes x RS_BLOCK)
+            static_assert(ITEMS == 16 || KEYGEN != 1, "text staging assumes 16 bytes per thread");
+            reinterpret_cast<uint4 *>(sb)[tid] = reinterpret_cast<const uint4 *>(text + tile_base)[tid];
+            if (tid < 8) sb[TILE + tid] = text[tile_base + TILE + tid];
+        } else {
+            for (u32 i = tid; i < TILE + 8; i += RS_BLOCK) {
+                u64 p = (u64)tile_base + i;
+                if (p >= n) p %= n;
+                sb[i] = text[p];
+            }
+        }
+        __syncthreads();
+        // window at byte o: three aligned words, funnel-shifted, then byte-swapped to big-endian order
+        const u32 *sw = reinterpret_cast<const u32 *>(sb);
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            u32 o = warp * (32u * ITEMS) + j * 32u + lane;
+            u32 w0 = sw[o >> 2], w1 = sw[(o >> 2) + 1], w2 = sw[(o >> 2) + 2];
+            u32 sh = (o & 3u) * 8u;
+            u32 first = __funnelshift_r(w0, w1, sh), second = __funnelshift_r(w1, w2, sh);
+            u64 k = ((u64)__byte_perm(first, 0, 0x0123) << 32) | __byte_perm(second, 0, 0x0123);
+            key[j] = (full_tile || tile_base + o < n) ? (KeyT)k : (KeyT)~(KeyT)0;
+        }
+    } else if (KEYGEN == 2) {
+        const u32 *rank = static_cast<const u32 *>(gen_src);
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            u32 idx = wbase + j * 32u + lane;
+            if (full_tile || idx < n) {
+                u32 i2 = idx + gen_k;             // < 2n <= 2^31
+                if (i2 >= n) i2 -= n;
+                key[j] = (KeyT)(((u64)rank[idx] << 32) | rank[i2]);
+            } else {
+                key[j] = (KeyT)~(KeyT)0;
+            }
+        }
+    } else if (full_tile) {
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) key[j] = keys_in[wbase + j * 32u + lane];
     } else {
@@ -268,7 +314,7 @@ template <typename K> static int set_smem_attr(bzap_ctx *ctx, K kernel, size_t b
 
 int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, u32 pass_mask, const u32 *d_hist, int hist_rows, bool vals_are_iota,
                      u64 **out_keys,
-                     u32 **out_vals, int *passes_run)
+                     u32 **out_vals, int *passes_run, const SortKeyGen *gen)
 {
     constexpr int ITEMS = RS_ITEMS_64;
     const int passes = 8;
@@ -292,13 +338,18 @@ int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, u32 pass_mask, const 
 
     auto k_iota = onesweep_pass_kernel<u64, ITEMS, true, true>;
     auto k_vals = onesweep_pass_kernel<u64, ITEMS, false, true>;
+    auto k_text = onesweep_pass_kernel<u64, ITEMS, true, true, 1>;
+    auto k_pair = onesweep_pass_kernel<u64, ITEMS, true, true, 2>;
     const size_t smem = sizeof(RsSmem<u64, ITEMS>);
     static bool attr_done = false;
     if (!attr_done) {
         RET(set_smem_attr(ctx, k_iota, smem));
         RET(set_smem_attr(ctx, k_vals, smem));
+        RET(set_smem_attr(ctx, k_text, smem));
+        RET(set_smem_attr(ctx, k_pair, smem));
         attr_done = true;
     }
+    if (gen && !vals_are_iota) return bzap_fail(ctx, BZAP_ERR_ARG, "key generation needs an identity payload");
     int cur = 0, run = 0;
     bool have_vals = !vals_are_iota;
     bool timed = false;
@@ -313,13 +364,22 @@ int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, u32 pass_mask, const 
             timed = true;
         }
         // algorithmic bytes: key 8 B read + 8 B written, payload 4 B written (+ 4 B read unless generated)
-        if (full) { ctx->stats.sort_bytes += (u64)n * (have_vals ? 24 : 20); ++ctx->stats.bwt_full_passes; }
-        if (!have_vals)
+        // (a text-window pass reads 1 B per key instead of 8)
+        if (full) {
+            ctx->stats.sort_bytes += (u64)n * (have_vals ? 24 : (gen && gen->mode == 1) ? 13 : 20);
+            ++ctx->stats.bwt_full_passes;
+        }
+        if (!have_vals && gen)
+            LAUNCH(ctx, (gen->mode == 1 ? k_text : k_pair), tiles, RS_BLOCK, smem, (const u64 *)nullptr, b->keys[cur ^ 1],
+                   (const u32 *)nullptr, b->vals[cur ^ 1], n, 8 * p, d_offsets + p * 256, d_status + (size_t)p * status_words,
+                   d_ticket + p, gen->src, gen->k);
+        else if (!have_vals)
             LAUNCH(ctx, k_iota, tiles, RS_BLOCK, smem, b->keys[cur], b->keys[cur ^ 1], (const u32 *)nullptr,
-                   b->vals[cur ^ 1], n, 8 * p, d_offsets + p * 256, d_status + (size_t)p * status_words, d_ticket + p);
+                   b->vals[cur ^ 1], n, 8 * p, d_offsets + p * 256, d_status + (size_t)p * status_words, d_ticket + p,
+                   (const void *)nullptr, 0u);
         else
             LAUNCH(ctx, k_vals, tiles, RS_BLOCK, smem, b->keys[cur], b->keys[cur ^ 1], b->vals[cur], b->vals[cur ^ 1], n,
-                   8 * p, d_offsets + p * 256, d_status + (size_t)p * status_words, d_ticket + p);
+                   8 * p, d_offsets + p * 256, d_status + (size_t)p * status_words, d_ticket + p, (const void *)nullptr, 0u);
         have_vals = true;
         cur ^= 1;
         ++run;
@@ -329,7 +389,7 @@ int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, u32 pass_mask, const 
         ctx->sort_ev_used += 2;
     }
     CU(ctx, cudaGetLastError());
-    *out_keys = b->keys[cur];
+    *out_keys = (gen && run == 0) ? nullptr : b->keys[cur];
     *out_vals = have_vals ? b->vals[cur] : nullptr;
     if (passes_run) *passes_run = run;
     return BZAP_OK;
@@ -362,7 +422,7 @@ int dev_sort_positions_by_byte(bzap_ctx *ctx, const u8 *d_bytes, u32 n, u32 *d_T
         attr_done = true;
     }
     LAUNCH(ctx, k, tiles, RS_BLOCK, smem, d_bytes, (u8 *)nullptr, (const u32 *)nullptr, d_T, n, 0, d_cum, d_status,
-           d_ticket);
+           d_ticket, (const void *)nullptr, 0u);
     CU(ctx, cudaGetLastError());
     return BZAP_OK;
 }
@@ -409,7 +469,8 @@ int dev_scatter_perm(bzap_ctx *ctx, const u32 *d_perm, const u32 *d_vals, u32 n,
     auto k = onesweep_pass_kernel<u32, ITEMS, false, true>;
     const size_t smem = sizeof(RsSmem<u32, ITEMS>);
     RET(set_smem_attr(ctx, k, smem));
-    LAUNCH(ctx, k, tiles, RS_BLOCK, smem, d_perm, d_tmp_idx, d_vals, d_tmp_vals, n, shift, d_offsets, d_status, d_ticket);
+    LAUNCH(ctx, k, tiles, RS_BLOCK, smem, d_perm, d_tmp_idx, d_vals, d_tmp_vals, n, shift, d_offsets, d_status, d_ticket,
+           (const void *)nullptr, 0u);
     LAUNCH(ctx, scatter_u32_kernel, sgrid, 256, 0, d_tmp_idx, d_tmp_vals, n, d_out);
     CU(ctx, cudaGetLastError());
     return BZAP_OK;
@@ -553,7 +614,8 @@ int dev_bucket_u32(bzap_ctx *ctx, const u32 *d_keys, const u32 *d_vals, u32 m, i
     auto k = onesweep_pass_kernel<u32, ITEMS, false, true>;
     const size_t smem = sizeof(RsSmem<u32, ITEMS>);
     RET(set_smem_attr(ctx, k, smem));
-    LAUNCH(ctx, k, tiles, RS_BLOCK, smem, d_keys, d_keys_out, d_vals, d_vals_out, m, shift, d_cum, d_status, d_ticket);
+    LAUNCH(ctx, k, tiles, RS_BLOCK, smem, d_keys, d_keys_out, d_vals, d_vals_out, m, shift, d_cum, d_status, d_ticket,
+           (const void *)nullptr, 0u);
     u32 *h = (u32 *)(ctx->mailbox + 28672);
     CU(ctx, cudaMemcpyAsync(h, d_hist, 256 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
