@@ -5,8 +5,9 @@
 //   * digit counts for all passes are known before the first pass: they come from the kernel that
 //     PRODUCES the keys (bwt.cu: one byte histogram, or the rank-digit histogram fused into the
 //     re-rank kernel), from radix_hist_u8 below, or in closed form (permutation payloads);
-//   * each 256-thread block takes a tile by atomic ticket, ranks its keys with warp-level
-//     match-any multisplit into per-warp shared-memory digit counters and publishes the tile's 256
+//   * each 256-thread block takes a tile by atomic ticket, ranks its keys with a warp-level
+//     multisplit (peer masks by MATCH.ANY or by eight votes, chosen per pass from the digit
+//     histogram) into per-warp shared-memory digit counters and publishes the tile's 256
 //     digit counts (flag+count in one 32-bit status word);
 //   * keys and payloads are regrouped by digit in shared memory; only then is the tile's global
 //     base per digit resolved by decoupled look-back over the previous tiles' status words, four
@@ -60,7 +61,7 @@ template <typename KeyT, int ITEMS, bool IOTA_VALS, bool WRITE_KEYS, int KEYGEN 
 __global__ void __launch_bounds__(RS_BLOCK, RS_MINBLOCKS)
 onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out, const u32 *__restrict__ vals_in,
                      u32 *__restrict__ vals_out, u32 n, int shift, const u32 *__restrict__ offsets, u32 *status,
-                     u32 *ticket, const void *__restrict__ gen_src = nullptr, u32 gen_k = 0)
+                     u32 *ticket, const void *__restrict__ gen_src, u32 gen_k, const u32 *__restrict__ rank_mode)
 {
     extern __shared__ __align__(16) u8 smem_raw[];
     RsSmem<KeyT, ITEMS> &S = *reinterpret_cast<RsSmem<KeyT, ITEMS> *>(smem_raw);
@@ -128,12 +129,14 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
     for (u32 i = lane; i < 256; i += 32) S.whist[warp][i] = 0;
     __syncwarp();
 
-    // warp-level multisplit: rank of each key among the warp's keys with the same digit
+    // warp-level multisplit: rank of each key among the warp's keys with the same digit.  The peer
+    // mask comes either from MATCH.ANY, whose cost on the SM-wide ADU pipe grows with the number of
+    // distinct digits in the warp (~30 cycles for text bytes, ~65 for uniform digits), or from eight
+    // votes, one per digit bit (flat cost, ~24 more instructions): *rank_mode says which one the
+    // digit distribution of this pass favours (radix_offsets_kernel).
     u32 *wh = S.whist[warp];
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) {
-        u32 d = digit_of(key[j], shift);
-        u32 m = __match_any_sync(FULL_MASK, d);
+    const bool by_votes = rank_mode != nullptr && *rank_mode != 0;     // uniform over the grid
+    auto rank_item = [&](int j, u32 d, u32 m) {
         u32 leader = (u32)__ffs(m) - 1u;
         u32 prev = 0;
         if (lane == leader) {
@@ -143,6 +146,26 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
         prev = __shfl_sync(FULL_MASK, prev, leader);
         rnk[j] = prev + (u32)__popc(m & lanemask_lt());
         __syncwarp();
+    };
+    if (by_votes) {
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            u32 d = digit_of(key[j], shift);
+            u32 m = FULL_MASK;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const bool bit = (d >> b) & 1u;
+                const u32 v = __ballot_sync(FULL_MASK, bit);
+                m &= bit ? v : ~v;
+            }
+            rank_item(j, d, m);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            u32 d = digit_of(key[j], shift);
+            rank_item(j, d, __match_any_sync(FULL_MASK, d));
+        }
     }
     __syncthreads();
 
@@ -237,11 +260,24 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
 }
 
 // ---- digit offsets -------------------------------------------------------------------------------
+#ifndef RS_VOTE_DISTINCT
+#define RS_VOTE_DISTINCT 20
+#endif
+// expected number of distinct digit values among the 32 keys of a warp, x 2^16, contribution of one
+// digit value that holds c of n keys: 1 - (1 - c/n)^32
+__device__ __forceinline__ u32 distinct32_term(u32 c, u32 n)
+{
+    float q = 1.0f - (float)c / (float)n;
+    q *= q; q *= q; q *= q; q *= q; q *= q;
+    return (u32)((1.0f - q) * 65536.0f);
+}
+
 // hist: hist_rows x 256 counts, pass p uses row p % hist_rows (several digits often share one
 // histogram, see bwt.cu).  offsets: passes x 256 exclusive sums.  trivial[p] = 1 when one digit
-// value holds all n keys (the pass is the identity permutation).
+// value holds all n keys (the pass is the identity permutation).  mode[p] = 1 when a warp is
+// expected to see at least RS_VOTE_DISTINCT distinct digits (rank by votes, see the pass kernel).
 __global__ void radix_offsets_kernel(const u32 *__restrict__ hist, int hist_rows, u32 *__restrict__ offsets, u32 *trivial,
-                                     u32 n, int passes)
+                                     u32 *mode, u32 n, int passes)
 {
     __shared__ u32 s_tmp[40];
     for (int p = 0; p < passes; ++p) {
@@ -250,6 +286,9 @@ __global__ void radix_offsets_kernel(const u32 *__restrict__ hist, int hist_rows
         u32 ex = block_exclusive_sum(c, s_tmp, &total);
         offsets[p * 256 + threadIdx.x] = ex;
         if (c == n) trivial[p] = 1;
+        u32 distinct;
+        block_exclusive_sum(distinct32_term(c, n), s_tmp, &distinct);
+        if (threadIdx.x == 0) mode[p] = distinct >= ((u32)RS_VOTE_DISTINCT << 16);
     }
 }
 
@@ -279,8 +318,8 @@ __global__ void __launch_bounds__(256) radix_hist_u8_kernel(const u8 *__restrict
     if (c) atomicAdd(&hist[threadIdx.x], c);
 }
 
-// cum[0..256]: exclusive byte counts (cum[256] = n)
-__global__ void radix_cum_u8_kernel(const u32 *__restrict__ hist, u32 *__restrict__ cum)
+// cum[0..256]: exclusive byte counts (cum[256] = n); mode as in radix_offsets_kernel
+__global__ void radix_cum_u8_kernel(const u32 *__restrict__ hist, u32 *__restrict__ cum, u32 *mode)
 {
     __shared__ u32 s_tmp[40];
     u32 c = hist[threadIdx.x];
@@ -288,6 +327,9 @@ __global__ void radix_cum_u8_kernel(const u32 *__restrict__ hist, u32 *__restric
     u32 ex = block_exclusive_sum(c, s_tmp, &total);
     cum[threadIdx.x] = ex;
     if (threadIdx.x == 255) cum[256] = ex + c;
+    u32 distinct;
+    block_exclusive_sum(distinct32_term(c, total), s_tmp, &distinct);
+    if (threadIdx.x == 0) *mode = distinct >= ((u32)RS_VOTE_DISTINCT << 16);
 }
 
 // ---- host drivers ------------------------------------------------------------------------------
@@ -320,12 +362,13 @@ int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, u32 pass_mask, const 
     const int passes = 8;
     const u32 tiles = (n + RS_BLOCK * ITEMS - 1) / (RS_BLOCK * ITEMS);
     const size_t status_words = (size_t)tiles * 256;
-    // control block: offsets[8][256], trivial[8], tickets[8], then status per pass
-    u32 *d_ctl = arena_get<u32>(ctx, 8 * 256 + 16 + passes * status_words);
+    // control block: offsets[8][256], trivial[8], tickets[8], ranking modes[8], then status per pass
+    u32 *d_ctl = arena_get<u32>(ctx, 8 * 256 + 24 + passes * status_words);
     if (!d_ctl) return bzap_fail(ctx, BZAP_ERR_NOMEM, "sort scratch");
-    u32 *d_offsets = d_ctl, *d_trivial = d_ctl + 8 * 256, *d_ticket = d_trivial + 8, *d_status = d_ticket + 8;
-    CU(ctx, cudaMemsetAsync(d_trivial, 0, (16 + passes * status_words) * sizeof(u32), ctx->stream));
-    LAUNCH(ctx, radix_offsets_kernel, 1, 256, 0, d_hist, hist_rows, d_offsets, d_trivial, n, passes);
+    u32 *d_offsets = d_ctl, *d_trivial = d_ctl + 8 * 256, *d_ticket = d_trivial + 8, *d_mode = d_ticket + 8,
+        *d_status = d_mode + 8;
+    CU(ctx, cudaMemsetAsync(d_trivial, 0, (24 + passes * status_words) * sizeof(u32), ctx->stream));
+    LAUNCH(ctx, radix_offsets_kernel, 1, 256, 0, d_hist, hist_rows, d_offsets, d_trivial, d_mode, n, passes);
     u32 *h_trivial = (u32 *)ctx->mailbox;
     if (n <= RS_SMALL_N) {
         // small inputs are launch / sync latency bound: a host round trip to learn which passes are
@@ -372,14 +415,15 @@ int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, u32 pass_mask, const 
         if (!have_vals && gen)
             LAUNCH(ctx, (gen->mode == 1 ? k_text : k_pair), tiles, RS_BLOCK, smem, (const u64 *)nullptr, b->keys[cur ^ 1],
                    (const u32 *)nullptr, b->vals[cur ^ 1], n, 8 * p, d_offsets + p * 256, d_status + (size_t)p * status_words,
-                   d_ticket + p, gen->src, gen->k);
+                   d_ticket + p, gen->src, gen->k, (const u32 *)(d_mode + p));
         else if (!have_vals)
             LAUNCH(ctx, k_iota, tiles, RS_BLOCK, smem, b->keys[cur], b->keys[cur ^ 1], (const u32 *)nullptr,
                    b->vals[cur ^ 1], n, 8 * p, d_offsets + p * 256, d_status + (size_t)p * status_words, d_ticket + p,
-                   (const void *)nullptr, 0u);
+                   (const void *)nullptr, 0u, (const u32 *)(d_mode + p));
         else
             LAUNCH(ctx, k_vals, tiles, RS_BLOCK, smem, b->keys[cur], b->keys[cur ^ 1], b->vals[cur], b->vals[cur ^ 1], n,
-                   8 * p, d_offsets + p * 256, d_status + (size_t)p * status_words, d_ticket + p, (const void *)nullptr, 0u);
+                   8 * p, d_offsets + p * 256, d_status + (size_t)p * status_words, d_ticket + p, (const void *)nullptr, 0u,
+                   (const u32 *)(d_mode + p));
         have_vals = true;
         cur ^= 1;
         ++run;
@@ -413,7 +457,7 @@ int dev_sort_positions_by_byte(bzap_ctx *ctx, const u8 *d_bytes, u32 n, u32 *d_T
     CU(ctx, cudaMemsetAsync(d_ctl, 0, (264 + status_words) * sizeof(u32), ctx->stream));
     u32 grid = min((n / 16 + 255) / 256 + 1, 148u * 8u);
     LAUNCH(ctx, radix_hist_u8_kernel, grid, 256, 0, d_bytes, n, d_hist);
-    LAUNCH(ctx, radix_cum_u8_kernel, 1, 256, 0, d_hist, d_cum);
+    LAUNCH(ctx, radix_cum_u8_kernel, 1, 256, 0, d_hist, d_cum, d_ticket + 1);
     auto k = onesweep_pass_kernel<u8, ITEMS, true, false>;
     const size_t smem = sizeof(RsSmem<u8, ITEMS>);
     static bool attr_done = false;
@@ -422,7 +466,7 @@ int dev_sort_positions_by_byte(bzap_ctx *ctx, const u8 *d_bytes, u32 n, u32 *d_T
         attr_done = true;
     }
     LAUNCH(ctx, k, tiles, RS_BLOCK, smem, d_bytes, (u8 *)nullptr, (const u32 *)nullptr, d_T, n, 0, d_cum, d_status,
-           d_ticket, (const void *)nullptr, 0u);
+           d_ticket, (const void *)nullptr, 0u, (const u32 *)(d_ticket + 1));
     CU(ctx, cudaGetLastError());
     return BZAP_OK;
 }
@@ -433,11 +477,12 @@ int dev_sort_positions_by_byte(bzap_ctx *ctx, const u8 *d_bytes, u32 n, u32 *d_T
 // target index (perm is a permutation of 0..n-1, so the digit histogram is known in closed form),
 // after which consecutive elements target one n/256-entry window that stays L2 resident and every
 // sector is written back exactly once.
-__global__ void perm_offsets_kernel(u32 n, int shift, u32 *offsets)
+__global__ void perm_offsets_kernel(u32 n, int shift, u32 *offsets, u32 *mode)
 {
     u64 d = threadIdx.x;
     u64 lo = d << shift;
     offsets[threadIdx.x] = (u32)(lo < n ? lo : n);
+    if (threadIdx.x == 0) *mode = 1;             // >= 128 equally likely digit values: rank by votes
 }
 
 __global__ void __launch_bounds__(256)
@@ -465,12 +510,12 @@ int dev_scatter_perm(bzap_ctx *ctx, const u32 *d_perm, const u32 *d_vals, u32 n,
     int bits = 0;
     while (((u64)1 << bits) < n) ++bits;          // n <= 2^bits
     const int shift = bits > 8 ? bits - 8 : 0;
-    LAUNCH(ctx, perm_offsets_kernel, 1, 256, 0, n, shift, d_offsets);
+    LAUNCH(ctx, perm_offsets_kernel, 1, 256, 0, n, shift, d_offsets, d_ticket + 1);
     auto k = onesweep_pass_kernel<u32, ITEMS, false, true>;
     const size_t smem = sizeof(RsSmem<u32, ITEMS>);
     RET(set_smem_attr(ctx, k, smem));
     LAUNCH(ctx, k, tiles, RS_BLOCK, smem, d_perm, d_tmp_idx, d_vals, d_tmp_vals, n, shift, d_offsets, d_status, d_ticket,
-           (const void *)nullptr, 0u);
+           (const void *)nullptr, 0u, (const u32 *)(d_ticket + 1));
     LAUNCH(ctx, scatter_u32_kernel, sgrid, 256, 0, d_tmp_idx, d_tmp_vals, n, d_out);
     CU(ctx, cudaGetLastError());
     return BZAP_OK;
@@ -610,12 +655,12 @@ int dev_bucket_u32(bzap_ctx *ctx, const u32 *d_keys, const u32 *d_vals, u32 m, i
     u32 *d_hist = d_ctl, *d_cum = d_ctl + 256, *d_ticket = d_ctl + 520, *d_status = d_ctl + 528;
     CU(ctx, cudaMemsetAsync(d_ctl, 0, (528 + status_words) * sizeof(u32), ctx->stream));
     LAUNCH(ctx, radix_hist_u32_digit_kernel, min((m + 255) / 256, 148u * 8u), 256, 0, d_keys, m, shift, d_hist);
-    LAUNCH(ctx, radix_cum_u8_kernel, 1, 256, 0, d_hist, d_cum);
+    LAUNCH(ctx, radix_cum_u8_kernel, 1, 256, 0, d_hist, d_cum, d_ticket + 1);
     auto k = onesweep_pass_kernel<u32, ITEMS, false, true>;
     const size_t smem = sizeof(RsSmem<u32, ITEMS>);
     RET(set_smem_attr(ctx, k, smem));
     LAUNCH(ctx, k, tiles, RS_BLOCK, smem, d_keys, d_keys_out, d_vals, d_vals_out, m, shift, d_cum, d_status, d_ticket,
-           (const void *)nullptr, 0u);
+           (const void *)nullptr, 0u, (const u32 *)(d_ticket + 1));
     u32 *h = (u32 *)(ctx->mailbox + 28672);
     CU(ctx, cudaMemcpyAsync(h, d_hist, 256 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
