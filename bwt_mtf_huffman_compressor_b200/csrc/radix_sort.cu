@@ -46,6 +46,21 @@ template <typename KeyT, int ITEMS> struct RsSmem {
     u32 ticket;
 };
 
+// m &= bit B of d set ? vote : ~vote, spelled out as bit test, select, VOTE and one three-input
+// LOP3 (m & ~(vote ^ s), s = all ones when the bit is set): the compiler's own lowering of the C
+// expression spends six instructions per bit (shift, and, compare, select, vote, combine)
+template <int B> __device__ __forceinline__ void vote_bit(u32 &m, u32 d)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t, v, s;\n\t"
+                 "and.b32 t, %1, %2;\n\t"
+                 "setp.ne.u32 p, t, 0;\n\t"
+                 "selp.b32 s, -1, 0, p;\n\t"
+                 "vote.sync.ballot.b32 v, p, 0xffffffff;\n\t"
+                 "lop3.b32 %0, %0, v, s, 0x90;\n\t}"
+                 : "+r"(m)
+                 : "r"(d), "n"(1 << B));
+}
+
 template <typename KeyT> __device__ __forceinline__ u32 digit_of(KeyT k, int shift)
 {
     return (u32)(k >> shift) & 0xffu;
@@ -152,12 +167,8 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
         for (int j = 0; j < ITEMS; ++j) {
             u32 d = digit_of(key[j], shift);
             u32 m = FULL_MASK;
-#pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                const bool bit = (d >> b) & 1u;
-                const u32 v = __ballot_sync(FULL_MASK, bit);
-                m &= bit ? v : ~v;
-            }
+            vote_bit<0>(m, d); vote_bit<1>(m, d); vote_bit<2>(m, d); vote_bit<3>(m, d);
+            vote_bit<4>(m, d); vote_bit<5>(m, d); vote_bit<6>(m, d); vote_bit<7>(m, d);
             rank_item(j, d, m);
         }
     } else {
@@ -261,7 +272,7 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
 
 // ---- digit offsets -------------------------------------------------------------------------------
 #ifndef RS_VOTE_DISTINCT
-#define RS_VOTE_DISTINCT 20
+#define RS_VOTE_DISTINCT 8
 #endif
 // expected number of distinct digit values among the 32 keys of a warp, x 2^16, contribution of one
 // digit value that holds c of n keys: 1 - (1 - c/n)^32
