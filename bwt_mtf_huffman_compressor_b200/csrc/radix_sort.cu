@@ -32,6 +32,9 @@
 #ifndef RS_SMALL_N
 #define RS_SMALL_N (1u << 19)
 #endif
+#ifndef RS_PREFETCH_TILES
+#define RS_PREFETCH_TILES 148
+#endif
 #define RS_WARPS (RS_BLOCK / 32)
 #define RS_FLAG_AGG (1u << 30)
 #define RS_FLAG_INCL (2u << 30)
@@ -141,6 +144,33 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
             key[j] = idx < n ? keys_in[idx] : (KeyT)~(KeyT)0;
         }
     }
+#if RS_PREFETCH_TILES > 0
+    // tiles are handed out in order, so the tile RS_PREFETCH_TILES ahead is started about one wave of
+    // resident blocks from now: pull its keys and payloads into L2 (one 128-byte line per request)
+    if (KEYGEN == 0) {
+        const u64 ptile = (u64)tile + RS_PREFETCH_TILES;
+        if ((ptile + 1) * TILE <= n) {
+            const char *kp = reinterpret_cast<const char *>(keys_in + ptile * TILE);
+            for (u32 o = tid * 128u; o < TILE * (u32)sizeof(KeyT); o += RS_BLOCK * 128u)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(kp + o));
+            if (!IOTA_VALS) {
+                const char *vp = reinterpret_cast<const char *>(vals_in + ptile * TILE);
+                for (u32 o = tid * 128u; o < TILE * 4u; o += RS_BLOCK * 128u)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(vp + o));
+            }
+        }
+    } else if (KEYGEN == 2) {
+        const u64 ptile = (u64)tile + RS_PREFETCH_TILES;
+        if ((ptile + 1) * TILE + gen_k <= n) {       // both rank windows without wrap-around
+            const char *r1 = reinterpret_cast<const char *>(static_cast<const u32 *>(gen_src) + ptile * TILE);
+            const char *r2 = r1 + (size_t)gen_k * 4u;
+            for (u32 o = tid * 128u; o < TILE * 4u; o += RS_BLOCK * 128u) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(r1 + o));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(r2 + o));
+            }
+        }
+    }
+#endif
     for (u32 i = lane; i < 256; i += 32) S.whist[warp][i] = 0;
     __syncwarp();
 
