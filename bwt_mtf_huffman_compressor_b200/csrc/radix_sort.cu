@@ -527,7 +527,7 @@ __global__ void perm_offsets_kernel(u32 n, int shift, u32 *offsets, u32 *mode)
 }
 
 #ifndef SC_BLOCKS_PER_SM
-#define SC_BLOCKS_PER_SM 4
+#define SC_BLOCKS_PER_SM 3
 #endif
 __global__ void __launch_bounds__(256)
 scatter_u32_kernel(const u32 *__restrict__ idx, const u32 *__restrict__ vals, u32 n, u32 *__restrict__ out)
