@@ -153,7 +153,8 @@ size_t scratch_bytes_decompress(size_t n, size_t payload)
 {
     // payload copy, mtf, last column, out | T | sort status | mtf tables | decode state
     return (payload + 4096) + 3 * (n + 1024) + 5 * n + sort_scratch_bytes((u32)n) + 2 * (n / 128 + 4096) * 768 +
-           (payload / 128 + 4096) * 32 + (8u << 20);
+           (payload / 128 + 4096) * 32 + (8u << 20) +
+           (n <= (2u << 20) ? 36 * n : 0);         // small blocks: 8-row splitter buckets in ibwt.cu (IB_SMALL_N)
 }
 
 // ---- header --------------------------------------------------------------------------------------------

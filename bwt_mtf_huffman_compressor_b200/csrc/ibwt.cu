@@ -9,7 +9,9 @@
 // T is a permutation and may have MANY cycles (periodic input: "abab" -> T = [2,3,0,1]); the walk
 // stays on the cycle of `primary` and laps it N / cycle_length times.  It is parallelised by
 // work-efficient list ranking with pseudo-random splitters:
-//   1. one splitter row per bucket of IB_STRIDE rows (hashed offset), plus `primary` itself;
+//   1. one splitter row per bucket of 2^slog rows (hashed offset), plus `primary` itself.  Large
+//      blocks use 64-row buckets; small ones (latency bound: the longest sub-list, ~ stride x ln(nodes)
+//      dependent loads, is what the walk waits for) use 8-row buckets;
 //   2. ibwt_walk_len_kernel : every splitter walks T until it lands on the next splitter ->
 //      reduced list (next splitter, sublist length);
 //   3. ibwt_wyllie_kernel   : pointer jumping on the reduced list, cut open at `primary`, gives
@@ -19,8 +21,9 @@
 // Nothing assumes a single list, so splitters on other cycles are simply never reached.
 #include "device_common.cuh"
 
-#define IB_STRIDE_LOG 6
-#define IB_STRIDE (1u << IB_STRIDE_LOG)
+#define IB_STRIDE_LOG_LARGE 6
+#define IB_STRIDE_LOG_SMALL 3
+#define IB_SMALL_N (2u << 20)
 #define IB_NIL 0xffffffffu
 
 __device__ __forceinline__ u32 ib_hash(u32 x)
@@ -31,19 +34,20 @@ __device__ __forceinline__ u32 ib_hash(u32 x)
     return x;
 }
 // row of the splitter of bucket b
-__device__ __forceinline__ u32 ib_splitter_row(u32 b, u32 n)
+__device__ __forceinline__ u32 ib_splitter_row(u32 b, u32 n, u32 slog)
 {
-    u32 lo = b << IB_STRIDE_LOG;
-    u32 span = min(IB_STRIDE, n - lo);
+    const u32 stride = 1u << slog;
+    u32 lo = b << slog;
+    u32 span = min(stride, n - lo);
     u32 h = ib_hash(b);
-    return lo + (span == IB_STRIDE ? (h & (IB_STRIDE - 1u)) : h % span);
+    return lo + (span == stride ? (h & (stride - 1u)) : h % span);
 }
 // node id of the splitter sitting on `row`, or IB_NIL.  Node `nb` (= number of buckets) is `primary`.
-__device__ __forceinline__ u32 ib_node_of(u32 row, u32 n, u32 nb, u32 primary)
+__device__ __forceinline__ u32 ib_node_of(u32 row, u32 n, u32 nb, u32 primary, u32 slog)
 {
     if (row == primary) return nb;
-    u32 b = row >> IB_STRIDE_LOG;
-    return ib_splitter_row(b, n) == row ? b : IB_NIL;
+    u32 b = row >> slog;
+    return ib_splitter_row(b, n, slog) == row ? b : IB_NIL;
 }
 
 // F(r): byte c with cum[c] <= r < cum[c+1].  A 4096-entry coarse table gives the first candidate
@@ -94,7 +98,7 @@ __device__ __forceinline__ u32 ib_first_col(const FirstCol &F, u32 r)
 #define IB_REFILL 8
 #define IB_SLOT 256
 __global__ void __launch_bounds__(256)
-ibwt_walk_len_kernel(const u32 *__restrict__ T, u32 n, u32 nb, u32 primary, const u32 *__restrict__ cum,
+ibwt_walk_len_kernel(const u32 *__restrict__ T, u32 n, u32 nb, u32 slog, u32 primary, const u32 *__restrict__ cum,
                      u64 *__restrict__ node, u8 *__restrict__ slots, u32 *__restrict__ resume, u32 *counter)
 {
     __shared__ FirstCol F;
@@ -113,7 +117,7 @@ ibwt_walk_len_kernel(const u32 *__restrict__ T, u32 n, u32 nb, u32 primary, cons
             if (j == IB_NIL) {
                 u32 mine = base + (u32)__popc(idle & lanemask_lt());
                 if (mine <= nb) {
-                    row = mine == nb ? primary : ib_splitter_row(mine, n);
+                    row = mine == nb ? primary : ib_splitter_row(mine, n, slog);
                     if (mine < nb && row == primary) node[mine] = ((u64)IB_NIL << 32);
                     else { j = mine; len = 0; }
                 }
@@ -125,7 +129,7 @@ ibwt_walk_len_kernel(const u32 *__restrict__ T, u32 n, u32 nb, u32 primary, cons
             else if (len == IB_SLOT) resume[j] = row;
             row = T[row];
             ++len;
-            u32 nx = ib_node_of(row, n, nb, primary);
+            u32 nx = ib_node_of(row, n, nb, primary, slog);
             if (nx != IB_NIL) {
                 // the list is cut open in front of `primary`: the node that reaches it becomes the tail
                 node[j] = ((u64)(nx == nb ? IB_NIL : nx) << 32) | len;
@@ -201,7 +205,8 @@ int dev_ibwt(bzap_ctx *ctx, const u8 *d_last, size_t n64, u64 primary64, u8 *d_o
     if (primary64 >= n64) return bzap_fail(ctx, BZAP_ERR_CORRUPT, "primary index %llu >= N %zu",
                                            (unsigned long long)primary64, n64);
     const u32 n = (u32)n64, primary = (u32)primary64;
-    const u32 nb = (n + IB_STRIDE - 1) >> IB_STRIDE_LOG;
+    const u32 slog = n <= IB_SMALL_N ? IB_STRIDE_LOG_SMALL : IB_STRIDE_LOG_LARGE;
+    const u32 nb = (u32)(((u64)n + (1u << slog) - 1) >> slog);
     const u32 nodes = nb + 1;
     u32 *d_T = arena_get<u32>(ctx, n);
     u32 *d_cum = arena_get<u32>(ctx, 260);
@@ -216,7 +221,7 @@ int dev_ibwt(bzap_ctx *ctx, const u8 *d_last, size_t n64, u64 primary64, u8 *d_o
     const u32 wgrid = nodes / 256 + 1 < 148u * 8u ? nodes / 256 + 1 : 148u * 8u;
     RET(dev_sort_positions_by_byte(ctx, d_last, n, d_T, d_cum));
     const u32 nblk = (nodes + 255) / 256;
-    LAUNCH(ctx, ibwt_walk_len_kernel, wgrid, 256, 0, d_T, n, nb, primary, d_cum, d_len, d_slots, d_resume, d_work);
+    LAUNCH(ctx, ibwt_walk_len_kernel, wgrid, 256, 0, d_T, n, nb, slog, primary, d_cum, d_len, d_slots, d_resume, d_work);
     // pointer jumping: after r rounds every node has jumped 2^r links
     int cur = 0;
     const u64 *src = d_len;
