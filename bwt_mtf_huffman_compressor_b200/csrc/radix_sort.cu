@@ -30,7 +30,7 @@
 #define RS_LB_WIDE 4
 #endif
 #ifndef RS_SMALL_N
-#define RS_SMALL_N (1u << 19)
+#define RS_SMALL_N (1u << 20)
 #endif
 #ifndef RS_PREFETCH_TILES
 #define RS_PREFETCH_TILES 148
@@ -318,19 +318,18 @@ __device__ __forceinline__ u32 distinct32_term(u32 c, u32 n)
 // value holds all n keys (the pass is the identity permutation).  mode[p] = 1 when a warp is
 // expected to see at least RS_VOTE_DISTINCT distinct digits (rank by votes, see the pass kernel).
 __global__ void radix_offsets_kernel(const u32 *__restrict__ hist, int hist_rows, u32 *__restrict__ offsets, u32 *trivial,
-                                     u32 *mode, u32 n, int passes)
+                                     u32 *mode, u32 n)
 {
     __shared__ u32 s_tmp[40];
-    for (int p = 0; p < passes; ++p) {
-        u32 c = hist[(p % hist_rows) * 256 + threadIdx.x];
-        u32 total;
-        u32 ex = block_exclusive_sum(c, s_tmp, &total);
-        offsets[p * 256 + threadIdx.x] = ex;
-        if (c == n) trivial[p] = 1;
-        u32 distinct;
-        block_exclusive_sum(distinct32_term(c, n), s_tmp, &distinct);
-        if (threadIdx.x == 0) mode[p] = distinct >= ((u32)RS_VOTE_DISTINCT << 16);
-    }
+    const int p = blockIdx.x;                    // one block per pass
+    u32 c = hist[(p % hist_rows) * 256 + threadIdx.x];
+    u32 total;
+    u32 ex = block_exclusive_sum(c, s_tmp, &total);
+    offsets[p * 256 + threadIdx.x] = ex;
+    if (c == n) trivial[p] = 1;
+    u32 distinct;
+    block_exclusive_sum(distinct32_term(c, n), s_tmp, &distinct);
+    if (threadIdx.x == 0) mode[p] = distinct >= ((u32)RS_VOTE_DISTINCT << 16);
 }
 
 // byte histogram for the inverse-BWT counting sort (u8 keys, one digit)
@@ -409,7 +408,7 @@ int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, u32 pass_mask, const 
     u32 *d_offsets = d_ctl, *d_trivial = d_ctl + 8 * 256, *d_ticket = d_trivial + 8, *d_mode = d_ticket + 8,
         *d_status = d_mode + 8;
     CU(ctx, cudaMemsetAsync(d_trivial, 0, (24 + passes * status_words) * sizeof(u32), ctx->stream));
-    LAUNCH(ctx, radix_offsets_kernel, 1, 256, 0, d_hist, hist_rows, d_offsets, d_trivial, d_mode, n, passes);
+    LAUNCH(ctx, radix_offsets_kernel, passes, 256, 0, d_hist, hist_rows, d_offsets, d_trivial, d_mode, n);
     u32 *h_trivial = (u32 *)ctx->mailbox;
     if (n <= RS_SMALL_N) {
         // small inputs are launch / sync latency bound: a host round trip to learn which passes are
