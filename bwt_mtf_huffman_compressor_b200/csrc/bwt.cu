@@ -310,10 +310,15 @@ bwt_collect_active_kernel(const u32 *__restrict__ rs, const u32 *__restrict__ sa
     }
 }
 
-// key[a] = (r1 << 32) | rank[(start + k) mod N] with the eight digit histograms (M is small here)
+// key[a] = (r1 << rshift) | rank[(start + k) mod N] with the eight digit histograms (M is small here).
+// rshift = bits of a rank (BWT_ACTIVE_PACK) packs the pair into 2 x bits: one radix pass fewer when
+// 2 x bits crosses a byte boundary less than 32 + bits does (26-bit ranks: 7 passes instead of 8).
+#ifndef BWT_ACTIVE_PACK
+#define BWT_ACTIVE_PACK 1
+#endif
 __global__ void __launch_bounds__(256)
 bwt_active_keys_kernel(const u32 *__restrict__ act_idx, const u32 *__restrict__ act_r1, u32 m, const u32 *__restrict__ rank,
-                       u32 n, u32 k, u64 *__restrict__ keys, u32 *hist8)
+                       u32 n, u32 k, u32 rshift, u64 *__restrict__ keys, u32 *hist8)
 {
     __shared__ u32 s_h[8 * 256];
     for (u32 i = threadIdx.x; i < 8 * 256; i += 256) s_h[i] = 0;
@@ -322,7 +327,7 @@ bwt_active_keys_kernel(const u32 *__restrict__ act_idx, const u32 *__restrict__ 
     for (u32 a = blockIdx.x * blockDim.x + threadIdx.x; a < m; a += gridDim.x * blockDim.x) {
         u32 j = act_idx[a] + kk;
         if (j >= n) j -= n;
-        u64 key = ((u64)act_r1[a] << 32) | rank[j];
+        u64 key = ((u64)act_r1[a] << rshift) | rank[j];
         keys[a] = key;
 #pragma unroll
         for (int p = 0; p < 8; ++p) atomicAdd(&s_h[p * 256 + ((u32)(key >> (8 * p)) & 0xffu)], 1u);
@@ -340,7 +345,7 @@ bwt_active_keys_kernel(const u32 *__restrict__ act_idx, const u32 *__restrict__ 
 //   newr[a]   = pos of the first element with the same (r1, r2)         (max-scan of sub-group heads)
 // pos is strictly increasing in a, so both scans are max-scans of monotone values.
 __global__ void __launch_bounds__(AC_BLOCK)
-bwt_active_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ idx, u32 m, u32 *__restrict__ sa,
+bwt_active_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ idx, u32 m, u32 rshift, u32 *__restrict__ sa,
                          u32 *__restrict__ rank, u32 *__restrict__ newr, u32 *__restrict__ pos_out,
                          u32 *counters /* [0]=groups [1]=sub groups */, u64 *status_g, u64 *status_s, u32 *ticket)
 {
@@ -358,7 +363,7 @@ bwt_active_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ i
 #pragma unroll
     for (int i = 0; i < AC_ITEMS; ++i) {
         u32 a = a0 + i;
-        bool gh = a < m && (a == 0 || (u32)(kcur[i + 1] >> 32) != (u32)(kcur[i] >> 32));
+        bool gh = a < m && (a == 0 || (u32)(kcur[i + 1] >> rshift) != (u32)(kcur[i] >> rshift));
         if (gh) { gcur = a + 1; ++ng; }
         gl[i] = gcur;
     }
@@ -377,7 +382,7 @@ bwt_active_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ i
     for (int i = 0; i < AC_ITEMS; ++i) {
         u32 a = a0 + i;
         u32 gs = max(gpre, gl[i]) - 1u;                      // index of the group's first active element
-        pos[i] = (u32)(kcur[i + 1] >> 32) + (a - gs);
+        pos[i] = (u32)(kcur[i + 1] >> rshift) + (a - gs);
         bool sh = a < m && (a == 0 || kcur[i + 1] != kcur[i]);
         if (sh) { scur = pos[i] + 1; ++ns; }
         sl[i] = scur;
@@ -497,18 +502,25 @@ static int bwt_active_rounds(bzap_ctx *ctx, u32 n, u32 m, u64 *k_io, const Activ
     u32 *h_cnt = (u32 *)(ctx->mailbox + 1024);
     SortBuffers ab = w.ab;
     u32 *act_r1 = w.act_r1, *next_idx = w.next_idx, *next_r1 = w.next_r1;
+#if BWT_ACTIVE_PACK
+    u32 rshift = 1;
+    while (rshift < 32 && (1ull << rshift) < n) ++rshift;            // ranks are < n <= 2^rshift
+    const u32 pass_mask = (1u << ((2 * rshift + 7) / 8)) - 1u;
+#else
+    const u32 rshift = 32, pass_mask = w.rank_mask;
+#endif
     while (m) {
         const u32 mt = (m + AC_TILE - 1) / AC_TILE;
         CU(ctx, cudaMemsetAsync(w.zero_base, 0, w.zero_bytes, ctx->stream));
         LAUNCH(ctx, bwt_active_keys_kernel, grid_for(m, 256, 148 * 4), 256, 0, ab.vals[0], act_r1, m, w.d_rank, n,
-               (u32)(k % n), ab.keys[0], w.d_hist8);
+               (u32)(k % n), rshift, ab.keys[0], w.d_hist8);
         int passes = 0;
         u64 *skeys = nullptr;
         u32 *sidx = nullptr;
         ctx->arena_off = w.arena_mark;
-        RET(dev_sort_pairs64(ctx, &ab, m, w.rank_mask, w.d_hist8, 8, false, &skeys, &sidx, &passes));
+        RET(dev_sort_pairs64(ctx, &ab, m, pass_mask, w.d_hist8, 8, false, &skeys, &sidx, &passes));
         *passes_total += (u32)passes;
-        LAUNCH(ctx, bwt_active_rerank_kernel, mt, AC_BLOCK, 0, skeys, sidx, m, w.sa_buf, w.d_rank, w.newr, w.pos, w.d_counters,
+        LAUNCH(ctx, bwt_active_rerank_kernel, mt, AC_BLOCK, 0, skeys, sidx, m, rshift, w.sa_buf, w.d_rank, w.newr, w.pos, w.d_counters,
                w.d_status, w.d_status + mt + 2, w.d_ticket);
         LAUNCH(ctx, bwt_active_compact_kernel, mt, AC_BLOCK, 0, w.newr, w.pos, sidx, m, next_idx, next_r1, w.d_counters + 2,
                w.cstatus, w.d_ticket + 1);
