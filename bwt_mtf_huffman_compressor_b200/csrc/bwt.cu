@@ -99,13 +99,16 @@ struct RrSmem {
 __global__ void __launch_bounds__(RR_BLOCK)
 bwt_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, u32 n, u32 ntiles, u32 pos_base,
                   u32 *__restrict__ rank,
-                  u32 *__restrict__ rs, u32 *hist4, u32 *counters /* [0]=groups [1]=singletons */, u64 *status,
+                  u32 *__restrict__ rs, u32 *hist4, u32 *counters /* [0]=groups [1]=singletons [2]=range ticket */, u64 *status,
                   u32 *block_active /* per block: rotations of its range still in a group > 1 (may be null) */)
 {
     __shared__ RrSmem S;
     const u32 tid = threadIdx.x;
+    // ranges are handed out by ticket, not by blockIdx: phase 2 waits on lower ranges, which then
+    // belong to blocks that already run (no assumption about the block dispatch order)
+    const u32 bid = take_ticket(counters + 2, &S.ticket);
     const u32 tpb = (ntiles + gridDim.x - 1) / gridDim.x;          // tiles per block
-    const u32 t0 = blockIdx.x * tpb, t1 = min(ntiles, t0 + tpb);
+    const u32 t0 = bid * tpb, t1 = min(ntiles, t0 + tpb);
     const u32 lo = t0 * RR_TILE, hi = min(n, t1 * RR_TILE);
     for (u32 i = tid; i < 4 * 256; i += RR_BLOCK) (&S.hist[0][0])[i] = 0;
     if (tid == 0) { S.heads = 0; S.singles = 0; S.tile_prefix = 0; }
@@ -127,18 +130,18 @@ bwt_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, u32 
             found = tot;
             end = beg;
         }
-        if (tid == 0) st_relaxed(&status[blockIdx.x], found ? (RR_FOUND | (u64)(found - 1)) : RR_NONE);
+        if (tid == 0) st_relaxed(&status[bid], found ? (RR_FOUND | (u64)(found - 1)) : RR_NONE);
     } else {
         if (tid == 0) {
-            st_relaxed(&status[blockIdx.x], RR_NONE);
-            if (block_active) block_active[blockIdx.x] = 0;
+            st_relaxed(&status[bid], RR_NONE);
+            if (block_active) block_active[bid] = 0;
         }
         return;
     }
     // 2. last head before the range (block 0 owns position 0, which is always a head)
     if (tid < 32) {
         u32 pre = 0;
-        int base = (int)blockIdx.x - 1;
+        int base = (int)bid - 1;
         while (base >= 0) {
             int t = base - (int)tid;
             u64 w = RR_NONE;
@@ -242,7 +245,7 @@ bwt_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ sa, u32 
     if (tid == 0) {
         if (S.heads) atomicAdd(&counters[0], S.heads);
         if (S.singles) atomicAdd(&counters[1], S.singles);
-        if (block_active) block_active[blockIdx.x] = (hi - lo) - S.singles;
+        if (block_active) block_active[bid] = (hi - lo) - S.singles;
     }
 }
 

@@ -28,6 +28,7 @@ struct bzap_ctx {
     int sort_ev_used = 0;
     bzap_stats stats = {};
     u64 launches = 0;
+    u32 attr_mask = 0;                  // per-device kernel attributes this context has already raised
     char err[256] = {0};
 };
 

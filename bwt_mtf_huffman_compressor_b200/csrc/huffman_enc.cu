@@ -242,10 +242,13 @@ int dev_huff_encode(bzap_ctx *ctx, const u8 *d_in, size_t n64, const CodeTable *
     words = (words + 3u) & ~3u;
     const size_t smem = (size_t)words * sizeof(u32);
     if (smem > 200 * 1024) return bzap_fail(ctx, BZAP_ERR_TOO_LARGE, "code length %d", ct->max_len);
-    // the attribute is per function, not per launch: contexts on other threads (batch API) may need
-    // a different size at the same time, so it is raised once to the largest size ever accepted
-    if (smem > 40 * 1024)
+    // the attribute is per function and device, not per launch: contexts on other threads (batch API)
+    // may need a different size at the same time, so every context raises it once to the largest
+    // size ever accepted
+    if (smem > 40 * 1024 && !(ctx->attr_mask & (1u << 8))) {
         CU(ctx, cudaFuncSetAttribute(huff_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        ctx->attr_mask |= 1u << 8;
+    }
     LAUNCH(ctx, huff_encode_kernel, tiles, ENC_BLOCK, smem, d_in, n, d_table, (u32 *)d_file, bit_base, d_status, d_ticket,
            words);
     CU(ctx, cudaGetLastError());

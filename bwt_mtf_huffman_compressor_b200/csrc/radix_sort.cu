@@ -388,6 +388,10 @@ size_t sort_scratch_bytes(u32 n)
     return 8 * (tiles * 256 * sizeof(u32) + 256) + 64 * 1024;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of the kernel: every context
+// (bound to one device, used by one thread at a time) raises it once for itself and remembers that
+// in its own bit mask, so a second context on another GPU of the same process is served as well
+enum { ATTR_SORT64 = 1u << 0, ATTR_SORT8 = 1u << 1, ATTR_SORT32 = 1u << 2 };
 template <typename K> static int set_smem_attr(bzap_ctx *ctx, K kernel, size_t bytes)
 {
     CU(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -424,13 +428,12 @@ int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, u32 pass_mask, const 
     auto k_text = onesweep_pass_kernel<u64, ITEMS, true, true, 1>;
     auto k_pair = onesweep_pass_kernel<u64, ITEMS, true, true, 2>;
     const size_t smem = sizeof(RsSmem<u64, ITEMS>);
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!(ctx->attr_mask & ATTR_SORT64)) {
         RET(set_smem_attr(ctx, k_iota, smem));
         RET(set_smem_attr(ctx, k_vals, smem));
         RET(set_smem_attr(ctx, k_text, smem));
         RET(set_smem_attr(ctx, k_pair, smem));
-        attr_done = true;
+        ctx->attr_mask |= ATTR_SORT64;
     }
     if (gen && !vals_are_iota) return bzap_fail(ctx, BZAP_ERR_ARG, "key generation needs an identity payload");
     int cur = 0, run = 0;
@@ -500,10 +503,9 @@ int dev_sort_positions_by_byte(bzap_ctx *ctx, const u8 *d_bytes, u32 n, u32 *d_T
     LAUNCH(ctx, radix_cum_u8_kernel, 1, 256, 0, d_hist, d_cum, d_ticket + 1);
     auto k = onesweep_pass_kernel<u8, ITEMS, true, false>;
     const size_t smem = sizeof(RsSmem<u8, ITEMS>);
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!(ctx->attr_mask & ATTR_SORT8)) {
         RET(set_smem_attr(ctx, k, smem));
-        attr_done = true;
+        ctx->attr_mask |= ATTR_SORT8;
     }
     LAUNCH(ctx, k, tiles, RS_BLOCK, smem, d_bytes, (u8 *)nullptr, (const u32 *)nullptr, d_T, n, 0, d_cum, d_status,
            d_ticket, (const void *)nullptr, 0u, (const u32 *)(d_ticket + 1));
@@ -560,7 +562,10 @@ int dev_scatter_perm(bzap_ctx *ctx, const u32 *d_perm, const u32 *d_vals, u32 n,
     LAUNCH(ctx, perm_offsets_kernel, 1, 256, 0, n, shift, d_offsets, d_ticket + 1);
     auto k = onesweep_pass_kernel<u32, ITEMS, false, true>;
     const size_t smem = sizeof(RsSmem<u32, ITEMS>);
-    RET(set_smem_attr(ctx, k, smem));
+    if (!(ctx->attr_mask & ATTR_SORT32)) {
+        RET(set_smem_attr(ctx, k, smem));
+        ctx->attr_mask |= ATTR_SORT32;
+    }
     LAUNCH(ctx, k, tiles, RS_BLOCK, smem, d_perm, d_tmp_idx, d_vals, d_tmp_vals, n, shift, d_offsets, d_status, d_ticket,
            (const void *)nullptr, 0u, (const u32 *)(d_ticket + 1));
     LAUNCH(ctx, scatter_u32_kernel, sgrid, 256, 0, d_tmp_idx, d_tmp_vals, n, d_out);
@@ -705,7 +710,10 @@ int dev_bucket_u32(bzap_ctx *ctx, const u32 *d_keys, const u32 *d_vals, u32 m, i
     LAUNCH(ctx, radix_cum_u8_kernel, 1, 256, 0, d_hist, d_cum, d_ticket + 1);
     auto k = onesweep_pass_kernel<u32, ITEMS, false, true>;
     const size_t smem = sizeof(RsSmem<u32, ITEMS>);
-    RET(set_smem_attr(ctx, k, smem));
+    if (!(ctx->attr_mask & ATTR_SORT32)) {
+        RET(set_smem_attr(ctx, k, smem));
+        ctx->attr_mask |= ATTR_SORT32;
+    }
     LAUNCH(ctx, k, tiles, RS_BLOCK, smem, d_keys, d_keys_out, d_vals, d_vals_out, m, shift, d_cum, d_status, d_ticket,
            (const void *)nullptr, 0u, (const u32 *)(d_ticket + 1));
     u32 *h = (u32 *)(ctx->mailbox + 28672);
