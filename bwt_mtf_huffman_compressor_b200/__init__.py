@@ -53,7 +53,8 @@ class Stats(C.Structure):
     _fields_ = [("ms_total", C.c_double), ("ms_bwt", C.c_double), ("ms_mtf", C.c_double), ("ms_huffman", C.c_double),
                 ("kernel_launches", C.c_uint64), ("bwt_rounds", C.c_uint32), ("bwt_sort_passes", C.c_uint32),
                 ("decode_sync_iters", C.c_uint32), ("bwt_full_passes", C.c_uint32), ("payload_bytes", C.c_uint64),
-                ("ms_sort", C.c_double), ("sort_bytes", C.c_uint64), ("sort_elems", C.c_uint64)]
+                ("ms_sort", C.c_double), ("sort_bytes", C.c_uint64), ("sort_elems", C.c_uint64),
+                ("ms_walk", C.c_double), ("walk_bytes", C.c_uint64)]
 
 
 _u8p = C.POINTER(C.c_uint8)

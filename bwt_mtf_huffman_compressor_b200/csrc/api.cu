@@ -338,6 +338,7 @@ static int decompress_any(bzap_ctx *ctx, const u8 *in, bool in_on_device, size_t
     ctx->stats.ms_mtf = ev_ms(ctx->ev[1], ctx->ev[2]);
     ctx->stats.ms_bwt = ev_ms(ctx->ev[2], ctx->ev[3]);
     ctx->stats.ms_total = ev_ms(ctx->ev[0], ctx->ev[3]);
+    ctx->stats.ms_walk = ev_ms(ctx->ev[4], ctx->ev[5]);
     ctx->stats.payload_bytes = payload_len;
     *out_len = (size_t)n;
     return BZAP_OK;

@@ -221,7 +221,10 @@ int dev_ibwt(bzap_ctx *ctx, const u8 *d_last, size_t n64, u64 primary64, u8 *d_o
     const u32 wgrid = nodes / 256 + 1 < 148u * 8u ? nodes / 256 + 1 : 148u * 8u;
     RET(dev_sort_positions_by_byte(ctx, d_last, n, d_T, d_cum));
     const u32 nblk = (nodes + 255) / 256;
+    CU(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
     LAUNCH(ctx, ibwt_walk_len_kernel, wgrid, 256, 0, d_T, n, nb, slog, primary, d_cum, d_len, d_slots, d_resume, d_work);
+    CU(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
+    ctx->stats.walk_bytes = 5ull * n;            // T[row] (4 B) read + one slot byte written per row
     // pointer jumping: after r rounds every node has jumped 2^r links
     int cur = 0;
     const u64 *src = d_len;

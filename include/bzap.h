@@ -67,6 +67,8 @@ typedef struct {
     double ms_sort;                         /* CUDA-event time inside onesweep passes of the last forward BWT */
     uint64_t sort_bytes;                    /* algorithmic bytes those passes moved (key+payload read+write) */
     uint64_t sort_elems;                    /* elements per pass (N) */
+    double ms_walk;                         /* CUDA-event time of the inverse BWT's list walk in the last decompress */
+    uint64_t walk_bytes;                    /* its algorithmic bytes: one 4-byte T entry per row + one output byte */
 } bzap_stats;
 
 /* ---- context ------------------------------------------------------------------------------ */

@@ -15,7 +15,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
 def test_reference_arm_prints_one_json_line():
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--size", str(4 << 20)],      # the default (the genuine 64 MiB block) takes ~90 s
                        capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stderr[-800:]
     lines = [l for l in p.stdout.splitlines() if l.strip()]
@@ -25,6 +26,8 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert 0.1 < d["value"] < 1000
+    assert d["cpu_baseline"]["cores"] == 1 and d["steps_measured"] == 1 and d["all_cores_slices"]["cores"] >= 1
+    assert d["config"]["block_bytes"] == 4 << 20
     for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config"):
         assert k in d
 
