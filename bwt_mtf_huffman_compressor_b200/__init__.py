@@ -57,6 +57,15 @@ class Stats(C.Structure):
                 ("ms_walk", C.c_double), ("walk_bytes", C.c_uint64)]
 
 
+class DistStats(C.Structure):
+    """bzap_dist_stats of include/bzap.h."""
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("rounds", C.c_uint32), ("reserved", C.c_uint32),
+                ("own_rotations", C.c_uint64), ("exchanged_bytes", C.c_uint64), ("ms_total", C.c_double),
+                ("ms_select_sort", C.c_double), ("ms_home", C.c_double), ("ms_rounds", C.c_double), ("ms_pull", C.c_double),
+                ("ms_round_sort", C.c_double), ("ms_tail", C.c_double)]
+
+
+COMM_ID_BYTES = 128
 _u8p = C.POINTER(C.c_uint8)
 _lib = None
 
@@ -99,6 +108,10 @@ def lib():
         "bzap_bytes_to_tree": (C.c_int, [_u8p, sz, C.POINTER(Tree)]),
         "bzap_huff_encode": (C.c_int, [vp, vp, sz, C.POINTER(Tree), vp, sz, szp]),
         "bzap_huff_decode": (C.c_int, [vp, vp, sz, C.POINTER(Tree), sz, vp]),
+        "bzap_comm_unique_id": (C.c_int, [_u8p]),
+        "bzap_ctx_comm_init": (C.c_int, [vp, _u8p, C.c_int, C.c_int]),
+        "bzap_compress_block_distributed": (C.c_int, [vp, vp, sz, vp, sz, szp]),
+        "bzap_get_dist_stats": (C.c_int, [vp, C.POINTER(DistStats)]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -149,6 +162,23 @@ class Context:
         _check(lib().bzap_get_stats(self.h, C.byref(s)), self.h)
         return s
 
+    # ---- one block over several GPUs (include/bzap.h: bzap_compress_block_distributed) ----
+    def comm_init(self, comm_id, world, rank):
+        """Collective: joins the NCCL communicator identified by the 128 bytes of comm_unique_id()."""
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(bytes(comm_id))
+        _check(lib().bzap_ctx_comm_init(self.h, buf, world, rank), self.h)
+
+    def compress_block_distributed(self, text_ptr, n, out_ptr, cap):
+        """Collective: device pointers; the file lands in rank 0's out buffer (returns its length, 0 elsewhere)."""
+        ln = C.c_size_t(0)
+        _check(lib().bzap_compress_block_distributed(self.h, C.c_void_p(text_ptr), n, C.c_void_p(out_ptr), cap, C.byref(ln)), self.h)
+        return ln.value
+
+    def dist_stats(self):
+        s = DistStats()
+        _check(lib().bzap_get_dist_stats(self.h, C.byref(s)), self.h)
+        return s
+
     # raw-pointer entry points used by bench.py (pinned host buffers / device buffers)
     def compress_ptr(self, in_ptr, n, out_ptr, cap, device=False):
         ln = C.c_size_t(0)
@@ -161,6 +191,15 @@ class Context:
         f = lib().bzap_decompress_device if device else lib().bzap_decompress
         _check(f(self.h, C.c_void_p(in_ptr), n, C.c_void_p(out_ptr), cap, C.byref(ln)), self.h)
         return ln.value
+
+
+def comm_unique_id():
+    """128 bytes naming a new communicator (rank 0 creates it and hands it to the other ranks)."""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    rc = lib().bzap_comm_unique_id(buf)
+    if rc != BZAP_OK:
+        raise BzapError(rc, "bzap_comm_unique_id")
+    return bytes(buf)
 
 
 _default_ctx = None

@@ -39,6 +39,7 @@ extern "C" const char *bzap_strerror(int code)
     case BZAP_ERR_ARG: return "bad argument";
     case BZAP_ERR_TOO_LARGE: return "block too large";
     case BZAP_ERR_NOMEM: return "out of memory";
+    case BZAP_ERR_NCCL: return "NCCL error (library missing or a collective failed)";
     default: return "unknown error";
     }
 }
@@ -71,6 +72,7 @@ extern "C" void bzap_ctx_destroy(bzap_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->own_stream) { cudaStreamSynchronize(c->own_stream); }
+    dist_comm_release(c);
     if (c->arena) cudaFree(c->arena);
     if (c->mailbox) cudaFreeHost(c->mailbox);
     for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);

@@ -275,7 +275,7 @@ __device__ __forceinline__ u32 compact_offset(u32 cnt, u32 tile, u64 *status, u3
 // Same contiguous ranges as bwt_rerank_kernel (same grid), whose per-block survivor counts give
 // every block its output offset directly: no look-back, a block scan per tile is all it takes.
 __global__ void __launch_bounds__(RR_BLOCK)
-bwt_collect_active_kernel(const u32 *__restrict__ rs, const u32 *__restrict__ sa, u32 n, u32 ntiles,
+bwt_collect_active_kernel(const u32 *__restrict__ rs, const u32 *__restrict__ sa, u32 n, u32 ntiles, u32 pos_base,
                           const u32 *__restrict__ block_active, u32 *__restrict__ act_idx, u32 *__restrict__ act_r1)
 {
     __shared__ u32 s_tmp[40];
@@ -291,7 +291,7 @@ bwt_collect_active_kernel(const u32 *__restrict__ rs, const u32 *__restrict__ sa
         const u32 j0 = tile * RR_TILE + tid * RR_ITEMS;
         u32 r[RR_ITEMS + 1];
 #pragma unroll
-        for (int i = 0; i <= RR_ITEMS; ++i) r[i] = j0 + i < n ? rs[j0 + i] : j0 + i;   // past the end counts as a head
+        for (int i = 0; i <= RR_ITEMS; ++i) r[i] = j0 + i < n ? rs[j0 + i] - pos_base : j0 + i;   // past the end counts as a head
         u32 keep = 0, cnt = 0;
 #pragma unroll
         for (int i = 0; i < RR_ITEMS; ++i) {
@@ -307,7 +307,7 @@ bwt_collect_active_kernel(const u32 *__restrict__ rs, const u32 *__restrict__ sa
         for (int i = 0; i < RR_ITEMS; ++i)
             if ((keep >> i) & 1u) {
                 act_idx[o] = sa ? sa[j0 + i] : j0 + i;
-                act_r1[o] = r[i];
+                act_r1[o] = r[i] + pos_base;
                 ++o;
             }
     }
@@ -348,7 +348,8 @@ bwt_active_keys_kernel(const u32 *__restrict__ act_idx, const u32 *__restrict__ 
 //   newr[a]   = pos of the first element with the same (r1, r2)         (max-scan of sub-group heads)
 // pos is strictly increasing in a, so both scans are max-scans of monotone values.
 __global__ void __launch_bounds__(AC_BLOCK)
-bwt_active_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ idx, u32 m, u32 rshift, u32 *__restrict__ sa,
+bwt_active_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ idx, u32 m, u32 rshift, u32 slot_base,
+                         u32 *__restrict__ sa,
                          u32 *__restrict__ rank, u32 *__restrict__ newr, u32 *__restrict__ pos_out,
                          u32 *counters /* [0]=groups [1]=sub groups */, u64 *status_g, u64 *status_s, u32 *ticket)
 {
@@ -404,8 +405,8 @@ bwt_active_rerank_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ i
         if (a < m) {
             u32 nr = max(spre, sl[i]) - 1u;
             u32 start = idx[a];
-            sa[pos[i]] = start;
-            rank[start] = nr;
+            sa[pos[i] - slot_base] = start;             // slot_base: first suffix-array slot this GPU holds
+            if (rank) rank[start] = nr;                 // nullptr: the ranks travel home by exchange
             newr[a] = nr;
             pos_out[a] = pos[i];
         }
@@ -482,20 +483,24 @@ static inline u32 grid_for(size_t work_items, u32 per_block, u32 cap = 148u * 16
 }
 
 // ---- active rounds, host loop ------------------------------------------------------------------------------
-struct ActiveWork {
-    SortBuffers ab;                       // key / payload ping-pong buffers for up to m elements
-    u32 *act_r1, *newr, *pos;             // per active element: group rank, new rank, suffix-array slot
-    u32 *next_idx, *next_r1;              // survivors of a round
-    u32 *sa_buf, *d_rank;                 // the block's suffix array and text-order ranks (updated in place)
-    u32 *d_hist8, *d_rrctl;
-    size_t rrctl_bytes;
-    u32 *d_counters, *d_ticket;
-    u64 *d_status, *cstatus;
-    size_t arena_mark;
-    u32 rank_mask;
-    u8 *zero_base;                        // hist8, rrctl and cstatus are allocated back to back:
-    size_t zero_bytes;                    // one memset per round clears all three
-};
+// One active round after its keys (r1 << rshift | r2), payloads (rotation starts) and the eight digit
+// histograms are in ab->keys[0] / ab->vals[0] / w.d_hist8: sort, new sparse ranks inside every group's
+// slot range of the suffix array (slot_base = first slot held by w.sa_buf; d_rank == nullptr when the
+// ranks travel home by exchange, dist_block.cu), survivors compacted into next_idx / next_r1.
+// Leaves w.d_counters = {groups, sub groups, survivors} on the device; no synchronisation.
+int bwt_active_sort_rerank(bzap_ctx *ctx, const ActiveWork &w, SortBuffers *ab, u32 m, u32 rshift, u32 pass_mask, u32 slot_base,
+                           u32 *d_rank, u32 *next_idx, u32 *next_r1, u64 **skeys, u32 **sidx, int *passes)
+{
+    const u32 mt = (m + AC_TILE - 1) / AC_TILE;
+    ctx->arena_off = w.arena_mark;
+    RET(dev_sort_pairs64(ctx, ab, m, pass_mask, w.d_hist8, 8, false, skeys, sidx, passes));
+    LAUNCH(ctx, bwt_active_rerank_kernel, mt, AC_BLOCK, 0, *skeys, *sidx, m, rshift, slot_base, w.sa_buf, d_rank, w.newr, w.pos,
+           w.d_counters, w.d_status, w.d_status + mt + 2, w.d_ticket);
+    LAUNCH(ctx, bwt_active_compact_kernel, mt, AC_BLOCK, 0, w.newr, w.pos, *sidx, m, next_idx, next_r1, w.d_counters + 2,
+           w.cstatus, w.d_ticket + 1);
+    CU(ctx, cudaGetLastError());
+    return BZAP_OK;
+}
 
 // w.ab.vals[0] / w.act_r1 hold the m unsettled rotations (start, group rank) in suffix-array order;
 // ranks reflect prefixes of length *k
@@ -513,20 +518,14 @@ static int bwt_active_rounds(bzap_ctx *ctx, u32 n, u32 m, u64 *k_io, const Activ
     const u32 rshift = 32, pass_mask = w.rank_mask;
 #endif
     while (m) {
-        const u32 mt = (m + AC_TILE - 1) / AC_TILE;
         CU(ctx, cudaMemsetAsync(w.zero_base, 0, w.zero_bytes, ctx->stream));
         LAUNCH(ctx, bwt_active_keys_kernel, grid_for(m, 256, 148 * 4), 256, 0, ab.vals[0], act_r1, m, w.d_rank, n,
                (u32)(k % n), rshift, ab.keys[0], w.d_hist8);
         int passes = 0;
         u64 *skeys = nullptr;
         u32 *sidx = nullptr;
-        ctx->arena_off = w.arena_mark;
-        RET(dev_sort_pairs64(ctx, &ab, m, pass_mask, w.d_hist8, 8, false, &skeys, &sidx, &passes));
+        RET(bwt_active_sort_rerank(ctx, w, &ab, m, rshift, pass_mask, 0u, w.d_rank, next_idx, next_r1, &skeys, &sidx, &passes));
         *passes_total += (u32)passes;
-        LAUNCH(ctx, bwt_active_rerank_kernel, mt, AC_BLOCK, 0, skeys, sidx, m, rshift, w.sa_buf, w.d_rank, w.newr, w.pos, w.d_counters,
-               w.d_status, w.d_status + mt + 2, w.d_ticket);
-        LAUNCH(ctx, bwt_active_compact_kernel, mt, AC_BLOCK, 0, w.newr, w.pos, sidx, m, next_idx, next_r1, w.d_counters + 2,
-               w.cstatus, w.d_ticket + 1);
         CU(ctx, cudaMemcpyAsync(h_cnt, w.d_counters, 3 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         ++*rounds;
@@ -686,7 +685,7 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
         u32 *next_idx = d_rs;                                  // rs is dead once the survivors are collected
         u32 *next_r1 = d_rs + half;
         CU(ctx, cudaMemsetAsync(d_rrctl, 0, rrctl_bytes, ctx->stream));
-        LAUNCH(ctx, bwt_collect_active_kernel, rr_grid, RR_BLOCK, 0, d_rs, sa, n, rr_tiles, d_bact, ab.vals[0], act_r1);
+        LAUNCH(ctx, bwt_collect_active_kernel, rr_grid, RR_BLOCK, 0, d_rs, sa, n, rr_tiles, 0u, d_bact, ab.vals[0], act_r1);
         ActiveWork w;
         w.ab = ab; w.act_r1 = act_r1; w.newr = newr; w.pos = pos; w.next_idx = next_idx; w.next_r1 = next_r1;
         w.sa_buf = sa_buf; w.d_rank = d_rank; w.d_hist8 = d_hist8; w.d_rrctl = d_rrctl; w.rrctl_bytes = rrctl_bytes;
@@ -736,6 +735,54 @@ int dev_rerank_run(bzap_ctx *ctx, const u64 *d_keys, u32 m, u32 pos_base, u32 *d
     counts[0] = h[0];
     counts[1] = h[1];
     return BZAP_OK;
+}
+
+// the same without a host round trip (dist_block.cu): d_ctl = rerank_ctl_words(m) zeroed words whose
+// words [1024] / [1025] end up holding {groups, singleton groups}; d_bact (148 * 6 + 8 words) receives the
+// per-range survivor counts that dev_collect_active consumes
+size_t rerank_ctl_words(u32 m)
+{
+    const u32 rr_tiles = (m + RR_TILE - 1) / RR_TILE;
+    return 4 * 256 + 8 + 2 * ((size_t)rr_tiles + 8);
+}
+int dev_rerank_sorted(bzap_ctx *ctx, const u64 *d_keys, u32 m, u32 pos_base, u32 *d_rs, u32 *d_ctl, u32 *d_bact)
+{
+    const u32 rr_tiles = (m + RR_TILE - 1) / RR_TILE;
+    u32 *d_hist4 = d_ctl, *d_counters = d_ctl + 4 * 256;
+    u64 *d_status = (u64 *)(d_ctl + 4 * 256 + 8);
+    LAUNCH(ctx, bwt_rerank_kernel, grid_for(rr_tiles, 1, 148 * 6), RR_BLOCK, 0, d_keys, (const u32 *)nullptr, m, rr_tiles,
+           pos_base, (u32 *)nullptr, d_rs, d_hist4, d_counters, d_status, d_bact);
+    CU(ctx, cudaGetLastError());
+    return BZAP_OK;
+}
+// rotations of a sorted run that still sit in a group > 1: (start, group rank), in slot order
+int dev_collect_active(bzap_ctx *ctx, const u32 *d_rs, const u32 *d_sa, u32 m, u32 pos_base, const u32 *d_bact, u32 *act_idx,
+                       u32 *act_r1)
+{
+    const u32 rr_tiles = (m + RR_TILE - 1) / RR_TILE;
+    LAUNCH(ctx, bwt_collect_active_kernel, grid_for(rr_tiles, 1, 148 * 6), RR_BLOCK, 0, d_rs, d_sa, m, rr_tiles, pos_base, d_bact,
+           act_idx, act_r1);
+    CU(ctx, cudaGetLastError());
+    return BZAP_OK;
+}
+size_t active_ctl_bytes(u32 m, ActiveWork *w, u8 *base)
+{
+    // hist8 | counters[4] ticket[4] | status x 2 | compaction status : one block, zeroed per round
+    const u32 mt = (m + AC_TILE - 1) / AC_TILE;
+    const size_t status_u64 = 2 * ((size_t)mt + 2) + 8;
+    const size_t bytes = 8 * 256 * sizeof(u32) + 8 * sizeof(u32) + status_u64 * sizeof(u64) + ((size_t)mt + 4) * sizeof(u64);
+    if (w && base) {
+        w->d_hist8 = (u32 *)base;
+        w->d_counters = w->d_hist8 + 8 * 256;
+        w->d_ticket = w->d_counters + 4;
+        w->d_status = (u64 *)(w->d_ticket + 4);
+        w->cstatus = w->d_status + status_u64;
+        w->zero_base = base;
+        w->zero_bytes = bytes;
+        w->d_rrctl = nullptr;
+        w->rrctl_bytes = 0;
+    }
+    return bytes;
 }
 
 // last[j] = text[(sa[j] + n - 1) mod n] for the m suffix-array slots held by this GPU
@@ -805,7 +852,7 @@ int dev_bwt_finish(bzap_ctx *ctx, const u8 *d_text, u32 n, u32 *d_sa, u32 *d_ran
         w.rank_mask = ((1u << nd) - 1u) | (((1u << nd) - 1u) << 4);
         w.zero_base = (u8 *)w.d_hist8;
         w.zero_bytes = (size_t)((u8 *)(w.cstatus + mt + 4) - (u8 *)w.d_hist8);
-        LAUNCH(ctx, bwt_collect_active_kernel, rr_grid, RR_BLOCK, 0, d_rs, d_sa, n, rr_tiles, d_bact, w.ab.vals[0], w.act_r1);
+        LAUNCH(ctx, bwt_collect_active_kernel, rr_grid, RR_BLOCK, 0, d_rs, d_sa, n, rr_tiles, 0u, d_bact, w.ab.vals[0], w.act_r1);
         RET(bwt_active_rounds(ctx, n, m, &k, w, &rounds, &passes_total));
     }
     LAUNCH(ctx, bwt_gather_kernel, grid_for((n + 3) / 4, 256), 256, 0, d_text, d_sa, n, d_last);

@@ -29,6 +29,11 @@ struct bzap_ctx {
     bzap_stats stats = {};
     u64 launches = 0;
     u32 attr_mask = 0;                  // per-device kernel attributes this context has already raised
+    // one block spread over several GPUs (dist_block.cu): NCCL communicator of the ranks that share it
+    void *comm = nullptr;               // ncclComm_t
+    int world = 1, rank = 0;
+    u8 *dist_host = nullptr;            // pinned staging for the small collectives
+    bzap_dist_stats dstats = {};
     char err[256] = {0};
 };
 
@@ -95,8 +100,18 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n, u8 *d_last, u64 *primary);
 // forward / inverse MTF (mtf.cu)
 int dev_mtf(bzap_ctx *ctx, const u8 *d_in, size_t n, u8 *d_out);
 int dev_imtf(bzap_ctx *ctx, const u8 *d_in, size_t n, u8 *d_out);
+// the forward transform in two phases, for a piece of a block that starts from a handed-over list (dist_block.cu)
+struct MtfPlan {
+    u32 n, chunk, nchunks, ngroups;
+    u32 *d_last, *d_gtot, *d_total;
+    u8 *d_lists;
+};
+size_t mtf_scratch_bytes(size_t n);
+int dev_mtf_begin(bzap_ctx *ctx, const u8 *d_in, size_t n, MtfPlan *plan);
+int dev_mtf_finish(bzap_ctx *ctx, const u8 *d_in, const MtfPlan *plan, const u32 *d_init, u8 *d_out);
 // histogram + first appearance order (huffman_enc.cu), syncs
 int dev_hist(bzap_ctx *ctx, const u8 *d_in, size_t n, u64 freq[256], u8 order[256], int *n_leaves);
+int dev_hist_launch(bzap_ctx *ctx, const u8 *d_in, u32 n, u64 *d_stat);   // no sync: 256 x u64 counts + 256 x u32 first positions
 // bit packer (huffman_enc.cu): ORs the code stream into d_file starting at bit `bit_base`
 // (d_file zeroed by the caller, 16-byte aligned, with >= 32 bytes of slack after the last bit)
 int dev_huff_encode(bzap_ctx *ctx, const u8 *d_in, size_t n, const CodeTable *ct, u8 *d_file, u64 bit_base);
@@ -105,6 +120,7 @@ int dev_huff_decode(bzap_ctx *ctx, const u8 *d_payload, size_t payload_len, cons
                     u8 *d_out);
 // inverse BWT (ibwt.cu)
 int dev_ibwt(bzap_ctx *ctx, const u8 *d_last, size_t n, u64 primary, u8 *d_out);
+void dist_comm_release(bzap_ctx *ctx);   // dist_block.cu: destroys the context's communicator, if any
 
 // ---- radix sort building blocks (radix_sort.cu) ----------------------------------------------
 // LSD onesweep over 64-bit keys with 32-bit payloads.  d_hist holds 8 x 256 digit counts already
@@ -125,6 +141,23 @@ struct SortKeyGen {
     const void *src;
     u32 k;
 };
+// state of the active-set rounds of the forward BWT (bwt.cu), shared with the distributed path
+struct ActiveWork {
+    SortBuffers ab;                       // key / payload ping-pong buffers for up to m elements
+    u32 *act_r1, *newr, *pos;             // per active element: group rank, new rank, suffix-array slot
+    u32 *next_idx, *next_r1;              // survivors of a round
+    u32 *sa_buf, *d_rank;                 // the block's suffix array and text-order ranks (updated in place)
+    u32 *d_hist8, *d_rrctl;
+    size_t rrctl_bytes;
+    u32 *d_counters, *d_ticket;
+    u64 *d_status, *cstatus;
+    size_t arena_mark;
+    u32 rank_mask;
+    u8 *zero_base;                        // hist8, rrctl and cstatus are allocated back to back:
+    size_t zero_bytes;                    // one memset per round clears all three
+};
+int bwt_active_sort_rerank(bzap_ctx *ctx, const ActiveWork &w, SortBuffers *ab, u32 m, u32 rshift, u32 pass_mask, u32 slot_base,
+                           u32 *d_rank, u32 *next_idx, u32 *next_r1, u64 **skeys, u32 **sidx, int *passes);
 int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, u32 pass_mask, const u32 *d_hist, int hist_rows, bool vals_are_iota,
                      u64 **out_keys, u32 **out_vals, int *passes_run, const SortKeyGen *gen = nullptr);
 // stable counting sort of positions by byte value: T[r] = position of the r-th smallest (byte, pos)
@@ -135,6 +168,11 @@ size_t sort_scratch_bytes(u32 n);
 int dev_init_keys(bzap_ctx *ctx, const u8 *d_text, u32 n, u32 lo, u32 m, u64 *d_keys);
 int dev_bwt_finish(bzap_ctx *ctx, const u8 *d_text, u32 n, u32 *d_sa, u32 *d_rank, u32 *d_rs, u64 k, u8 *d_last, u64 *primary);
 int dev_rerank_run(bzap_ctx *ctx, const u64 *d_keys, u32 m, u32 pos_base, u32 *d_rs, u32 counts[2]);
+size_t rerank_ctl_words(u32 m);
+int dev_rerank_sorted(bzap_ctx *ctx, const u64 *d_keys, u32 m, u32 pos_base, u32 *d_rs, u32 *d_ctl, u32 *d_bact);
+int dev_collect_active(bzap_ctx *ctx, const u32 *d_rs, const u32 *d_sa, u32 m, u32 pos_base, const u32 *d_bact, u32 *act_idx,
+                       u32 *act_r1);
+size_t active_ctl_bytes(u32 m, ActiveWork *w, u8 *base);   // lays the per-round control block of the active rounds out at base
 int dev_sort_pairs_generic(bzap_ctx *ctx, u64 *d_keys, u32 *d_vals, u32 m, u64 *d_keys_tmp, u32 *d_vals_tmp,
                            int *result_in_tmp);
 int dev_permute_pairs(bzap_ctx *ctx, const u64 *d_keys, const u32 *d_vals, const u32 *d_perm, u32 m, u64 *d_out_k, u32 *d_out_v);
@@ -144,6 +182,12 @@ int dev_bucket_u32(bzap_ctx *ctx, const u32 *d_keys, const u32 *d_vals, u32 m, i
                    u32 h_counts[256]);
 int dev_partition_dest(bzap_ctx *ctx, const u64 *d_keys, const u32 *d_vals, u32 m, const u64 *h_sk, const u32 *h_sv, int ns,
                        u8 *d_dest);
+size_t bucket_ctl_words(u32 m);
+int dev_bucket_pass_u64(bzap_ctx *ctx, const u64 *d_keys, const u32 *d_vals, u32 m, int shift, u64 *d_keys_out, u32 *d_vals_out,
+                        const u32 *d_hist256, u32 *d_ctl);
+int dev_bucket_pass_u32(bzap_ctx *ctx, const u32 *d_keys, const u32 *d_vals, u32 m, int shift, u32 *d_keys_out, u32 *d_vals_out,
+                        u32 *d_hist256, u32 *d_ctl);
+int dev_scatter_offset_async(bzap_ctx *ctx, const u32 *d_idx, const u32 *d_vals, u32 m, u32 off, u32 *d_out);
 // 256-bin byte histogram accumulated into d_hist256 (caller zeroes it)
 int dev_byte_hist(bzap_ctx *ctx, const u8 *d_bytes, u32 n, u32 *d_hist256);
 // out[perm[j]] = vals[j] for a permutation perm of 0..n-1; tmp buffers hold n u32 each

@@ -52,6 +52,19 @@ hist_first_kernel(const u8 *__restrict__ in, u32 n, unsigned long long *freq, u3
     }
 }
 
+// device part only: d_stat = 256 x u64 counts followed by 256 x u32 first positions (0xffffffff = absent)
+int dev_hist_launch(bzap_ctx *ctx, const u8 *d_in, u32 n, u64 *d_stat)
+{
+    u32 *d_first = (u32 *)(d_stat + 256);
+    CU(ctx, cudaMemsetAsync(d_stat, 0, 256 * sizeof(u64), ctx->stream));
+    CU(ctx, cudaMemsetAsync(d_first, 0xff, 256 * sizeof(u32), ctx->stream));
+    if (n == 0) return BZAP_OK;
+    u32 grid = (u32)((n / 16 + 255) / 256 + 1);
+    if (grid > 148 * 8) grid = 148 * 8;
+    LAUNCH(ctx, hist_first_kernel, grid, 256, 0, d_in, n, (unsigned long long *)d_stat, d_first);
+    return BZAP_OK;
+}
+
 int dev_hist(bzap_ctx *ctx, const u8 *d_in, size_t n64, u64 freq[256], u8 order[256], int *n_leaves)
 {
     if (n64 == 0) return bzap_fail(ctx, BZAP_ERR_EMPTY, "empty input");
@@ -59,12 +72,7 @@ int dev_hist(bzap_ctx *ctx, const u8 *d_in, size_t n64, u64 freq[256], u8 order[
     const u32 n = (u32)n64;
     u64 *d_freq = arena_get<u64>(ctx, 256 + 128);
     if (!d_freq) return bzap_fail(ctx, BZAP_ERR_NOMEM, "hist scratch");
-    u32 *d_first = (u32 *)(d_freq + 256);
-    CU(ctx, cudaMemsetAsync(d_freq, 0, 256 * sizeof(u64), ctx->stream));
-    CU(ctx, cudaMemsetAsync(d_first, 0xff, 256 * sizeof(u32), ctx->stream));
-    u32 grid = (u32)((n / 16 + 255) / 256 + 1);
-    if (grid > 148 * 8) grid = 148 * 8;
-    LAUNCH(ctx, hist_first_kernel, grid, 256, 0, d_in, n, (unsigned long long *)d_freq, d_first);
+    RET(dev_hist_launch(ctx, d_in, n, d_freq));
     u64 *h = (u64 *)(ctx->mailbox + 2048);
     CU(ctx, cudaMemcpyAsync(h, d_freq, 256 * sizeof(u64) + 256 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));

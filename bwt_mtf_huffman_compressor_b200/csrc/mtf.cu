@@ -77,8 +77,10 @@ __device__ __forceinline__ u32 imtf_step(u32 *list, u32 v)
 }
 
 // ---- forward ---------------------------------------------------------------------------------------
-// last[chunk][sym] = 256 + position of the last occurrence of sym inside the chunk (0 = absent).
-// The table must be zero on entry.
+// last[chunk][sym] = MTF_KEY_BASE + position of the last occurrence of sym inside the chunk (0 = absent).
+// The table must be zero on entry.  Keys 1..256 are left to a start list handed over from another GPU
+// (dist_block.cu): position i of that list carries key 256 - i.
+#define MTF_KEY_BASE 257u
 __global__ void __launch_bounds__(MTF_THREADS)
 mtf_last_kernel(const u8 *__restrict__ in, u32 n, u32 chunk, u32 nchunks, u32 *__restrict__ last)
 {
@@ -97,7 +99,7 @@ mtf_last_kernel(const u8 *__restrict__ in, u32 n, u32 chunk, u32 nchunks, u32 *_
         --p;
         u32 s = in[p];
         u32 w = s_seen[s >> 5][threadIdx.x], bit = 1u << (s & 31u);
-        if (!(w & bit)) { s_seen[s >> 5][threadIdx.x] = w | bit; row[s] = p + 256u; ++found; }
+        if (!(w & bit)) { s_seen[s >> 5][threadIdx.x] = w | bit; row[s] = p + MTF_KEY_BASE; ++found; }
     }
     while (p > beg && found < 256) {
         p -= 16;
@@ -107,7 +109,7 @@ mtf_last_kernel(const u8 *__restrict__ in, u32 n, u32 chunk, u32 nchunks, u32 *_
         for (int q = 15; q >= 0; --q) {
             u32 s = (ws[q >> 2] >> (8 * (q & 3))) & 0xffu;
             u32 w = s_seen[s >> 5][threadIdx.x], bit = 1u << (s & 31u);
-            if (!(w & bit)) { s_seen[s >> 5][threadIdx.x] = w | bit; row[s] = p + q + 256u; ++found; }
+            if (!(w & bit)) { s_seen[s >> 5][threadIdx.x] = w | bit; row[s] = p + q + MTF_KEY_BASE; ++found; }
         }
     }
 }
@@ -129,7 +131,9 @@ __global__ void __launch_bounds__(256) mtf_scan_group_kernel(u32 *__restrict__ l
     group_tot[(size_t)g * 256 + s] = run;
 }
 
-__global__ void __launch_bounds__(256) mtf_scan_top_kernel(u32 *__restrict__ group_tot, u32 ngroups)
+// total (may be null): the "last occurrence" summary of the whole input, i.e. what a following
+// piece of the same block needs to know about this one
+__global__ void __launch_bounds__(256) mtf_scan_top_kernel(u32 *__restrict__ group_tot, u32 ngroups, u32 *__restrict__ total)
 {
     const u32 s = threadIdx.x;
     u32 run = 0;
@@ -141,6 +145,7 @@ __global__ void __launch_bounds__(256) mtf_scan_top_kernel(u32 *__restrict__ gro
         for (int i = 0; i < 8; ++i)
             if (g + i < ngroups) { group_tot[(size_t)(g + i) * 256 + s] = run; run = max(run, v[i]); }
     }
+    if (total) total[s] = run;
 }
 
 // one warp per chunk.  key[s] = last occurrence of symbol s before the chunk (0 = never seen).
@@ -148,7 +153,8 @@ __global__ void __launch_bounds__(256) mtf_scan_top_kernel(u32 *__restrict__ gro
 // seen symbols (a few dozen on text) need ranking: they are compacted first, each is ranked against
 // the compacted keys, and an unseen symbol's slot follows from ballots alone.
 __global__ void __launch_bounds__(256)
-mtf_lists_kernel(const u32 *__restrict__ last, const u32 *__restrict__ group_tot, u32 nchunks, u8 *__restrict__ lists)
+mtf_lists_kernel(const u32 *__restrict__ last, const u32 *__restrict__ group_tot, const u32 *__restrict__ init, u32 nchunks,
+                 u8 *__restrict__ lists)
 {
     __shared__ __align__(16) u32 s_key[8][256];
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -161,6 +167,7 @@ mtf_lists_kernel(const u32 *__restrict__ last, const u32 *__restrict__ group_tot
     for (int i = 0; i < 8; ++i) {
         u32 s = lane + 32u * i;                       // symbols in increasing order over (i, lane)
         u32 k = max(last[(size_t)c * 256 + s], group_tot[(size_t)g * 256 + s]);
+        if (init) k = max(k, init[s]);
         key[i] = k;
         u32 m = __ballot_sync(FULL_MASK, k != 0);
         seen_below[i] = nseen + (u32)__popc(m & lanemask_lt());     // seen symbols smaller than s
@@ -325,27 +332,57 @@ static u32 pick_chunk(u32 n)
     return c;
 }
 
+size_t mtf_scratch_bytes(size_t n)
+{
+    const u32 chunk = pick_chunk((u32)n);
+    const size_t nchunks = (n + chunk - 1) / chunk + 2;
+    return nchunks * 1280 + (nchunks / MTF_GROUP + 2) * 1024 + 8192;
+}
+
+// phase 1: per-chunk "last occurrence" tables and their scans; plan->d_total[256] = summary of the whole input
+int dev_mtf_begin(bzap_ctx *ctx, const u8 *d_in, size_t n64, MtfPlan *plan)
+{
+    if (n64 > BZAP_MAX_BLOCK) return bzap_fail(ctx, BZAP_ERR_TOO_LARGE, "block of %zu bytes", n64);
+    const u32 n = (u32)n64;
+    plan->n = n;
+    plan->chunk = pick_chunk(n);
+    plan->nchunks = (n + plan->chunk - 1) / plan->chunk;
+    plan->ngroups = (plan->nchunks + MTF_GROUP - 1) / MTF_GROUP;
+    plan->d_last = arena_get<u32>(ctx, (size_t)plan->nchunks * 256 + 256);
+    plan->d_gtot = arena_get<u32>(ctx, (size_t)plan->ngroups * 256 + 256);
+    plan->d_lists = arena_get<u8>(ctx, (size_t)plan->nchunks * 256 + 256);
+    plan->d_total = arena_get<u32>(ctx, 256);
+    if (!plan->d_last || !plan->d_gtot || !plan->d_lists || !plan->d_total) return bzap_fail(ctx, BZAP_ERR_NOMEM, "mtf scratch");
+    if (n == 0) {
+        CU(ctx, cudaMemsetAsync(plan->d_total, 0, 256 * sizeof(u32), ctx->stream));
+        return BZAP_OK;
+    }
+    const u32 cblocks = (plan->nchunks + MTF_THREADS - 1) / MTF_THREADS;
+    CU(ctx, cudaMemsetAsync(plan->d_last, 0, (size_t)plan->nchunks * 256 * sizeof(u32), ctx->stream));
+    LAUNCH(ctx, mtf_last_kernel, cblocks, MTF_THREADS, 0, d_in, n, plan->chunk, plan->nchunks, plan->d_last);
+    LAUNCH(ctx, mtf_scan_group_kernel, plan->ngroups, 256, 0, plan->d_last, plan->nchunks, plan->d_gtot);
+    LAUNCH(ctx, mtf_scan_top_kernel, 1, 256, 0, plan->d_gtot, plan->ngroups, plan->d_total);
+    CU(ctx, cudaGetLastError());
+    return BZAP_OK;
+}
+// phase 2: start lists and the transform itself; d_init (may be null) = keys of the list the input starts
+// from when it is not the identity of main.cpp:96-97 (a later piece of a block spread over several GPUs)
+int dev_mtf_finish(bzap_ctx *ctx, const u8 *d_in, const MtfPlan *plan, const u32 *d_init, u8 *d_out)
+{
+    if (plan->n == 0) return BZAP_OK;
+    const u32 cblocks = (plan->nchunks + MTF_THREADS - 1) / MTF_THREADS;
+    LAUNCH(ctx, mtf_lists_kernel, (plan->nchunks + 7) / 8, 256, 0, plan->d_last, plan->d_gtot, d_init, plan->nchunks, plan->d_lists);
+    LAUNCH(ctx, mtf_apply_kernel, cblocks, MTF_THREADS, 0, d_in, plan->n, plan->chunk, plan->nchunks, plan->d_lists, d_out);
+    CU(ctx, cudaGetLastError());
+    return BZAP_OK;
+}
+
 int dev_mtf(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_out)
 {
     if (n64 == 0) return BZAP_OK;
-    if (n64 > BZAP_MAX_BLOCK) return bzap_fail(ctx, BZAP_ERR_TOO_LARGE, "block of %zu bytes", n64);
-    const u32 n = (u32)n64;
-    const u32 chunk = pick_chunk(n);
-    const u32 nchunks = (n + chunk - 1) / chunk;
-    const u32 ngroups = (nchunks + MTF_GROUP - 1) / MTF_GROUP;
-    u32 *d_last = arena_get<u32>(ctx, (size_t)nchunks * 256);
-    u32 *d_gtot = arena_get<u32>(ctx, (size_t)ngroups * 256);
-    u8 *d_lists = arena_get<u8>(ctx, (size_t)nchunks * 256);
-    if (!d_last || !d_gtot || !d_lists) return bzap_fail(ctx, BZAP_ERR_NOMEM, "mtf scratch");
-    const u32 cblocks = (nchunks + MTF_THREADS - 1) / MTF_THREADS;
-    CU(ctx, cudaMemsetAsync(d_last, 0, (size_t)nchunks * 256 * sizeof(u32), ctx->stream));
-    LAUNCH(ctx, mtf_last_kernel, cblocks, MTF_THREADS, 0, d_in, n, chunk, nchunks, d_last);
-    LAUNCH(ctx, mtf_scan_group_kernel, ngroups, 256, 0, d_last, nchunks, d_gtot);
-    LAUNCH(ctx, mtf_scan_top_kernel, 1, 256, 0, d_gtot, ngroups);
-    LAUNCH(ctx, mtf_lists_kernel, (nchunks + 7) / 8, 256, 0, d_last, d_gtot, nchunks, d_lists);
-    LAUNCH(ctx, mtf_apply_kernel, cblocks, MTF_THREADS, 0, d_in, n, chunk, nchunks, d_lists, d_out);
-    CU(ctx, cudaGetLastError());
-    return BZAP_OK;
+    MtfPlan plan;
+    RET(dev_mtf_begin(ctx, d_in, n64, &plan));
+    return dev_mtf_finish(ctx, d_in, &plan, nullptr, d_out);
 }
 
 int dev_imtf(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_out)

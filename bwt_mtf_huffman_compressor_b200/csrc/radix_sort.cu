@@ -391,7 +391,7 @@ size_t sort_scratch_bytes(u32 n)
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of the kernel: every context
 // (bound to one device, used by one thread at a time) raises it once for itself and remembers that
 // in its own bit mask, so a second context on another GPU of the same process is served as well
-enum { ATTR_SORT64 = 1u << 0, ATTR_SORT8 = 1u << 1, ATTR_SORT32 = 1u << 2 };
+enum { ATTR_SORT64 = 1u << 0, ATTR_SORT8 = 1u << 1, ATTR_SORT32 = 1u << 2, ATTR_SORT64B = 1u << 3 };
 template <typename K> static int set_smem_attr(bzap_ctx *ctx, K kernel, size_t bytes)
 {
     CU(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -721,5 +721,62 @@ int dev_bucket_u32(bzap_ctx *ctx, const u32 *d_keys, const u32 *d_vals, u32 m, i
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaGetLastError());
     memcpy(h_counts, h, 256 * sizeof(u32));
+    return BZAP_OK;
+}
+
+// ---- single bucketing passes without a host round trip (dist_block.cu) ------------------------------------
+// Stable regroup of (key, payload) by the 8-bit digit (key >> shift) & 255.  d_hist256 holds the digit
+// counts (device; for the u32 form they are counted here).  d_ctl: bucket_ctl_words(m) words of scratch.
+size_t bucket_ctl_words(u32 m)
+{
+    const size_t t64 = ((size_t)m + RS_BLOCK * RS_ITEMS_64 - 1) / (RS_BLOCK * RS_ITEMS_64);
+    const size_t t32 = ((size_t)m + RS_BLOCK * RS_ITEMS_32 - 1) / (RS_BLOCK * RS_ITEMS_32);
+    return 264 + 8 + (t64 > t32 ? t64 : t32) * 256;
+}
+int dev_bucket_pass_u64(bzap_ctx *ctx, const u64 *d_keys, const u32 *d_vals, u32 m, int shift, u64 *d_keys_out, u32 *d_vals_out,
+                        const u32 *d_hist256, u32 *d_ctl)
+{
+    constexpr int ITEMS = RS_ITEMS_64;
+    const u32 tiles = (m + RS_BLOCK * ITEMS - 1) / (RS_BLOCK * ITEMS);
+    u32 *d_cum = d_ctl, *d_ticket = d_ctl + 264, *d_status = d_ctl + 272;
+    CU(ctx, cudaMemsetAsync(d_ticket, 0, (8 + (size_t)tiles * 256) * sizeof(u32), ctx->stream));
+    LAUNCH(ctx, radix_cum_u8_kernel, 1, 256, 0, d_hist256, d_cum, d_ticket + 1);
+    auto k = onesweep_pass_kernel<u64, ITEMS, false, true>;
+    const size_t smem = sizeof(RsSmem<u64, ITEMS>);
+    if (!(ctx->attr_mask & ATTR_SORT64B)) {
+        RET(set_smem_attr(ctx, k, smem));
+        ctx->attr_mask |= ATTR_SORT64B;
+    }
+    LAUNCH(ctx, k, tiles, RS_BLOCK, smem, d_keys, d_keys_out, d_vals, d_vals_out, m, shift, d_cum, d_status, d_ticket,
+           (const void *)nullptr, 0u, (const u32 *)(d_ticket + 1));
+    CU(ctx, cudaGetLastError());
+    return BZAP_OK;
+}
+int dev_bucket_pass_u32(bzap_ctx *ctx, const u32 *d_keys, const u32 *d_vals, u32 m, int shift, u32 *d_keys_out, u32 *d_vals_out,
+                        u32 *d_hist256, u32 *d_ctl)
+{
+    constexpr int ITEMS = RS_ITEMS_32;
+    const u32 tiles = (m + RS_BLOCK * ITEMS - 1) / (RS_BLOCK * ITEMS);
+    u32 *d_cum = d_ctl, *d_ticket = d_ctl + 264, *d_status = d_ctl + 272;
+    CU(ctx, cudaMemsetAsync(d_ticket, 0, (8 + (size_t)tiles * 256) * sizeof(u32), ctx->stream));
+    CU(ctx, cudaMemsetAsync(d_hist256, 0, 256 * sizeof(u32), ctx->stream));
+    LAUNCH(ctx, radix_hist_u32_digit_kernel, min((m + 255) / 256, 148u * 8u), 256, 0, d_keys, m, shift, d_hist256);
+    LAUNCH(ctx, radix_cum_u8_kernel, 1, 256, 0, d_hist256, d_cum, d_ticket + 1);
+    auto k = onesweep_pass_kernel<u32, ITEMS, false, true>;
+    const size_t smem = sizeof(RsSmem<u32, ITEMS>);
+    if (!(ctx->attr_mask & ATTR_SORT32)) {
+        RET(set_smem_attr(ctx, k, smem));
+        ctx->attr_mask |= ATTR_SORT32;
+    }
+    LAUNCH(ctx, k, tiles, RS_BLOCK, smem, d_keys, d_keys_out, d_vals, d_vals_out, m, shift, d_cum, d_status, d_ticket,
+           (const void *)nullptr, 0u, (const u32 *)(d_ticket + 1));
+    CU(ctx, cudaGetLastError());
+    return BZAP_OK;
+}
+// out[idx[j] - off] = vals[j], no synchronisation
+int dev_scatter_offset_async(bzap_ctx *ctx, const u32 *d_idx, const u32 *d_vals, u32 m, u32 off, u32 *d_out)
+{
+    if (m == 0) return BZAP_OK;
+    LAUNCH(ctx, scatter_offset_kernel, min((m + 255) / 256, 148u * (u32)SC_BLOCKS_PER_SM), 256, 0, d_idx, d_vals, m, off, d_out);
     return BZAP_OK;
 }

@@ -33,6 +33,7 @@ extern "C" {
 #define BZAP_ERR_ARG         -6  /* NULL pointer / bad argument                                 */
 #define BZAP_ERR_TOO_LARGE   -7  /* block larger than BZAP_MAX_BLOCK, or code word > 64 bits    */
 #define BZAP_ERR_NOMEM       -8
+#define BZAP_ERR_NCCL        -9  /* NCCL missing, or a collective failed                        */
 
 #define BZAP_MAX_BLOCK   ((size_t)1 << 30)   /* one BWT block = whole input (README.md:40)      */
 #define BZAP_HEADER_BYTES 24                 /* io_utilities.h:17-19                            */
@@ -70,6 +71,16 @@ typedef struct {
     double ms_walk;                         /* CUDA-event time of the inverse BWT's list walk in the last decompress */
     uint64_t walk_bytes;                    /* its algorithmic bytes: one 4-byte T entry per row + one output byte */
 } bzap_stats;
+
+/* one block sorted over the GPUs of one box: phase timings (CUDA events on this rank's stream) */
+typedef struct {
+    int32_t world, rank;
+    uint32_t rounds;                        /* prefix-doubling rounds, the 8-byte key sort included  */
+    uint32_t reserved;
+    uint64_t own_rotations;                 /* rotations whose 8-byte key this rank owns             */
+    uint64_t exchanged_bytes;               /* bytes this rank sent to peers (all phases)            */
+    double ms_total, ms_select_sort, ms_home, ms_rounds, ms_pull, ms_round_sort, ms_tail;
+} bzap_dist_stats;
 
 /* ---- context ------------------------------------------------------------------------------ */
 int  bzap_ctx_create(int device, bzap_ctx **out);
@@ -172,6 +183,29 @@ int bzap_dev_gather_last(bzap_ctx *ctx, const uint8_t *d_text, size_t n, const u
 /* the stages after bwt() (main.cpp:309-324): last column + primary index -> reference-format file    */
 int bzap_compress_from_bwt_device(bzap_ctx *ctx, const uint8_t *d_last, size_t n, uint64_t primary, uint8_t *d_out,
                                   size_t out_cap, size_t *out_len);
+
+
+/* ---- ONE block sorted over several GPUs (BASELINE config 5 ii) -----------------------
+ * Replaces bwt() + move_to_front() + huffman() + write_bytes() (main.cpp:304-324) for a block that
+ * is spread over the GPUs of one box: one process (or thread) per GPU, each with its own context;
+ * the contexts share an NCCL communicator that the library creates and owns.
+ *   rank 0:      bzap_comm_unique_id(id)  -> hand the 128 bytes to the other ranks (any transport)
+ *   every rank:  bzap_ctx_comm_init(ctx, id, world, rank)          (collective)
+ *   every rank:  bzap_compress_block_distributed(ctx, d_text, n, d_out, cap, &len)   (collective)
+ * d_text: the whole block, resident on every GPU.  The file (byte-identical to bzap_compress) lands
+ * in rank 0's d_out; the other ranks pass d_out = NULL and get *out_len = 0.
+ * Distributed prefix doubling: rank g owns the rotations whose first 8 bytes fall into its key range
+ * (splitters from a hashed sample), sorts them locally and keeps their suffix-array slots; per round
+ * only unsettled rotations pull rank[(i+k) mod N] from the rank that owns text position i+k
+ * (request / response all-to-all over NVLink) and send their new ranks home; MTF start lists, the
+ * Huffman statistics and the bit offsets of the payload pieces are exchanged by all-gather.
+ * A context without a communicator is a world of one (same code, no NCCL needed).                  */
+#define BZAP_COMM_ID_BYTES 128
+int bzap_comm_unique_id(uint8_t id[BZAP_COMM_ID_BYTES]);
+int bzap_ctx_comm_init(bzap_ctx *ctx, const uint8_t id[BZAP_COMM_ID_BYTES], int world, int rank);
+int bzap_compress_block_distributed(bzap_ctx *ctx, const uint8_t *d_text, size_t n, uint8_t *d_out, size_t out_cap,
+                                    size_t *out_len);
+int bzap_get_dist_stats(bzap_ctx *ctx, bzap_dist_stats *out);
 
 #ifdef __cplusplus
 }

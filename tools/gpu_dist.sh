@@ -1,11 +1,17 @@
 #!/bin/bash
+# distributed single block on an N-GPU lease: parity tests, then timings.  $1 = N, $2 = sizes (space separated)
+N=${1:-2}; SIZES=${2:-"268435456 1073741824"}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_distributed.py -m gpu -q --tb=short -x 2>&1 | tail -30 > gpurun_out/dist_test.log
-tail -6 gpurun_out/dist_test.log
-N=$(nvidia-smi -L | wc -l)
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tools/bench_block.py --size 268435456 --check > gpurun_out/block_${N}.json 2> gpurun_out/block_${N}.err
-echo "block rc=$?"; cat gpurun_out/block_${N}.json; tail -3 gpurun_out/block_${N}.err
-if [ "$N" -gt 1 ]; then
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_${N}.json 2> gpurun_out/bench_${N}.err
-echo "bench N=$N rc=$?"; cat gpurun_out/bench_${N}.json | cut -c1-600; tail -3 gpurun_out/bench_${N}.err
-fi
+timeout 900 python -m pytest tests/test_gpu_distributed.py -m gpu -x -q --tb=short 2>&1 | tail -15 | tee gpurun_out/dist_test_n$N.log
+for S in $SIZES; do
+  for G in 1 2 4 8; do
+    if [ $G -le $N ]; then
+      if [ $G -eq 1 ]; then
+        BZAP_DIST_TIMING=$TIMING timeout 600 python tools/bench_block.py --size $S --single 2>gpurun_out/blk.err | tee -a gpurun_out/block_n$N.jsonl
+      else
+        timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29571 tools/bench_block.py --size $S 2>gpurun_out/blk.err | tee -a gpurun_out/block_n$N.jsonl
+      fi
+      tail -3 gpurun_out/blk.err
+    fi
+  done
+done
