@@ -225,6 +225,9 @@ def run_ours(args):
         clocks["remeasured_after_throttle"] = remeasured
 
     cal = None if args.no_calgary else calgary_batch(bz, W, rank, world, dist)
+    del d_in, d_file, d_back
+    torch.cuda.empty_cache()
+    blk = None if args.no_block1g else single_block(bz, W, ctx, rank, world, local, dist, args.block_size)
 
     t = torch.tensor([dev_ms, host_ms, 0.0 if golden_ok else 1.0], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -276,6 +279,7 @@ def run_ours(args):
                 "note": "N dependent random 4-byte reads of T: bound by random 32-byte-sector accesses, not by streaming bandwidth"},
             "clocks": clocks,
             "calgary_batch": cal,
+            "single_block_1g": blk,
         }
         prof = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(prof):
@@ -292,6 +296,52 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def single_block(bz, W, ctx, rank, world, local, dist, n):
+    """BASELINE config 5 (ii): ONE 1 GiB text block (seed 0x5EED1024) compressed by all N GPUs together --
+    strong scaling.  N = 1: bzap_compress_device.  N > 1: bzap_compress_block_distributed (distributed
+    prefix doubling, NCCL all-to-all over NVLink, csrc/dist_block.cu); the text is resident on every GPU
+    and the file lands on rank 0.  Device-timed (CUDA events inside the library), max over ranks, mean
+    of two runs after one warm-up; the file must equal the oracle golden (tests/golden/golden.json)."""
+    import torch
+    data = W.synthetic_text(n, 0x5EED1024)
+    text = torch.from_numpy(data).cuda()
+    del data
+    cap = bz.compress_bound(n)
+    out = torch.empty(cap if rank == 0 else 16, dtype=torch.uint8, device="cuda")
+    if world > 1:
+        box = [bz.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(box[0], world, rank)
+    ms, rounds, ln = [], 0, 0
+    for it in range(3):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if world == 1:
+            ln = ctx.compress_ptr(text.data_ptr(), n, out.data_ptr(), cap, device=True)
+            st = ctx.stats()
+            t, rounds = st.ms_total, st.bwt_rounds
+        else:
+            ln = ctx.compress_block_distributed(text.data_ptr(), n, out.data_ptr() if rank == 0 else 0, cap)
+            st = ctx.dist_stats()
+            t, rounds = st.ms_total, st.rounds
+        if it > 0:
+            ms.append(t)
+    tt = torch.tensor(ms, dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    sec = float(tt.mean()) * 1e-3
+    if rank != 0:
+        return None
+    sha = hashlib.sha256(out[:ln].cpu().numpy().tobytes()).hexdigest()
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))["text"].get(str(n))
+    return {"block_bytes": n, "n_gpus": world, "seconds": round(sec, 4), "MBps": round(n / sec / 1e6, 1), "rounds": int(rounds),
+            "compressed_bytes": int(ln), "sha256": sha,
+            "matches_golden": bool(g is not None and g.get("seed") == "0x5EED1024" and sha == g["sha256"]),
+            "path": "bzap_compress_device" if world == 1 else "bzap_compress_block_distributed (NCCL, %d ranks)" % world,
+            "scaling": "strong", "timing": "CUDA events inside the library, text resident in HBM on every rank, max over ranks"}
 
 
 def calgary_batch(bz, W, rank, world, dist):
@@ -446,6 +496,8 @@ def main():
     ap.add_argument("--size", type=int, default=N_TEXT)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-calgary", action="store_true", help="skip the Calgary batch (profiling runs)")
+    ap.add_argument("--no-block1g", action="store_true", help="skip the single 1 GiB block (profiling runs)")
+    ap.add_argument("--block-size", type=int, default=1 << 30)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

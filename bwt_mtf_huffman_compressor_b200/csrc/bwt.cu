@@ -451,26 +451,26 @@ __global__ void iota_kernel(u32 *out, u32 n)
 }
 
 // ---- last column --------------------------------------------------------------------------------------
-// L[j] = text[(SA[j] + N - 1) mod N]   (main.cpp:87); sa == nullptr means SA = identity
-__global__ void __launch_bounds__(256) bwt_gather_kernel(const u8 *__restrict__ text, const u32 *__restrict__ sa, u32 n,
+// L[j] = text[(SA[j] + N - 1) mod N], j < m   (main.cpp:87); sa == nullptr means SA = identity
+__global__ void __launch_bounds__(256) bwt_gather_kernel(const u8 *__restrict__ text, const u32 *__restrict__ sa, u32 n, u32 m,
                                                          u8 *__restrict__ last)
 {
-    const u32 nq = (n + 3) / 4;
+    const u32 nq = (m + 3) / 4;
     for (u32 q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
         u32 w = 0;
         u32 j0 = q * 4;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             u32 j = j0 + b;
-            if (j < n) {
+            if (j < m) {
                 u32 s = sa ? sa[j] : j;
                 u32 c = text[s == 0 ? n - 1 : s - 1];
                 w |= c << (8 * b);
             }
         }
-        if (j0 + 3 < n) *reinterpret_cast<u32 *>(last + j0) = w;
+        if (j0 + 3 < m) *reinterpret_cast<u32 *>(last + j0) = w;
         else
-            for (u32 b = 0; j0 + b < n; ++b) last[j0 + b] = (u8)(w >> (8 * b));
+            for (u32 b = 0; j0 + b < m; ++b) last[j0 + b] = (u8)(w >> (8 * b));
     }
 }
 
@@ -696,7 +696,7 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
         RET(bwt_active_rounds(ctx, n, active, &k, w, &rounds, &passes_total));
         sa = sa_buf;
     }
-    LAUNCH(ctx, bwt_gather_kernel, grid_for((n + 3) / 4, 256), 256, 0, d_in, sa, n, d_last);
+    LAUNCH(ctx, bwt_gather_kernel, grid_for((n + 3) / 4, 256), 256, 0, d_in, sa, n, n, d_last);
     u32 *h_primary = (u32 *)(ctx->mailbox + 1040);
     CU(ctx, cudaMemcpyAsync(h_primary, d_rank, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -796,7 +796,8 @@ bwt_gather_slots_kernel(const u8 *__restrict__ text, const u32 *__restrict__ sa,
 }
 int dev_gather_slots(bzap_ctx *ctx, const u8 *d_text, const u32 *d_sa, u32 n, u32 m, u8 *d_last)
 {
-    LAUNCH(ctx, bwt_gather_slots_kernel, grid_for(m, 256), 256, 0, d_text, d_sa, n, m, d_last);
+    if (((uintptr_t)d_last & 3) == 0) LAUNCH(ctx, bwt_gather_kernel, grid_for((m + 3) / 4, 256), 256, 0, d_text, d_sa, n, m, d_last);
+    else LAUNCH(ctx, bwt_gather_slots_kernel, grid_for(m, 256), 256, 0, d_text, d_sa, n, m, d_last);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaGetLastError());
     return BZAP_OK;
@@ -855,7 +856,7 @@ int dev_bwt_finish(bzap_ctx *ctx, const u8 *d_text, u32 n, u32 *d_sa, u32 *d_ran
         LAUNCH(ctx, bwt_collect_active_kernel, rr_grid, RR_BLOCK, 0, d_rs, d_sa, n, rr_tiles, 0u, d_bact, w.ab.vals[0], w.act_r1);
         RET(bwt_active_rounds(ctx, n, m, &k, w, &rounds, &passes_total));
     }
-    LAUNCH(ctx, bwt_gather_kernel, grid_for((n + 3) / 4, 256), 256, 0, d_text, d_sa, n, d_last);
+    LAUNCH(ctx, bwt_gather_kernel, grid_for((n + 3) / 4, 256), 256, 0, d_text, d_sa, n, n, d_last);
     u32 *h_primary = (u32 *)(ctx->mailbox + 1040);
     CU(ctx, cudaMemcpyAsync(h_primary, d_rank, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));

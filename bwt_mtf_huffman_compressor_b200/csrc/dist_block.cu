@@ -201,15 +201,21 @@ __device__ __forceinline__ u64 dist_window(const u32 *sw, u32 o)
     return ((u64)__byte_perm(first, 0, 0x0123) << 32) | __byte_perm(second, 0, 0x0123);
 }
 
+// Both text sweeps give every block a CONTIGUOUS range of tiles: the count sweep records how many own
+// rotations each range holds, so the select sweep knows every range's output offset up front -- no
+// look-back between tiles (a tile does so little work here that a look-back degenerates into a chain:
+// 5.9 ms for 1 GiB of text with one ticketed tile per block).
 // counts[0] = rotations with key < lo_key (owned by lower ranks), counts[1] = rotations in [lo_key, hi_key)
 __global__ void __launch_bounds__(DB_BLOCK)
-dist_owner_count_kernel(const u8 *__restrict__ text, u32 n, u64 lo_key, u64 hi_key, int hi_open, u32 *counts)
+dist_owner_count_kernel(const u8 *__restrict__ text, u32 n, u64 lo_key, u64 hi_key, int hi_open, u32 tiles, u32 *counts,
+                        u32 *__restrict__ range_cnt)
 {
     __shared__ __align__(16) u8 sb[DB_TILE + 16];
     __shared__ u32 s_tmp[40];
-    const u32 tiles = (n + DB_TILE - 1) / DB_TILE;
+    const u32 tpb = (tiles + gridDim.x - 1) / gridDim.x;
+    const u32 t0 = blockIdx.x * tpb, t1 = min(tiles, t0 + tpb);
     u32 below = 0, mine = 0;
-    for (u32 tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    for (u32 tile = t0; tile < t1; ++tile) {
         const u32 base = tile * DB_TILE;
         __syncthreads();
         dist_stage_tile(text, n, base, sb);
@@ -229,53 +235,56 @@ dist_owner_count_kernel(const u8 *__restrict__ text, u32 n, u64 lo_key, u64 hi_k
     block_exclusive_sum(below, s_tmp, &tb);
     block_exclusive_sum(mine, s_tmp, &tm);
     if (threadIdx.x == 0) {
+        range_cnt[blockIdx.x] = tm;
         if (tb) atomicAdd(&counts[0], tb);
         if (tm) atomicAdd(&counts[1], tm);
     }
 }
 
-// own rotations, in text order: keys[], starts[] and the eight digit histograms of the keys
+// own rotations, in text order: keys[], starts[] and the eight digit histograms of the keys (same grid as the count sweep)
 __global__ void __launch_bounds__(DB_BLOCK)
-dist_select_kernel(const u8 *__restrict__ text, u32 n, u64 lo_key, u64 hi_key, int hi_open, u64 *__restrict__ keys,
-                   u32 *__restrict__ starts, u32 *hist8, u64 *status, u32 *ticket)
+dist_select_kernel(const u8 *__restrict__ text, u32 n, u64 lo_key, u64 hi_key, int hi_open, u32 tiles,
+                   const u32 *__restrict__ range_cnt, u64 *__restrict__ keys, u32 *__restrict__ starts, u32 *hist8)
 {
     __shared__ __align__(16) u8 sb[DB_TILE + 16];
     __shared__ u32 s_h[8 * 256];
     __shared__ u32 s_tmp[40];
-    __shared__ u32 s_ticket, s_base;
     for (u32 i = threadIdx.x; i < 8 * 256; i += DB_BLOCK) s_h[i] = 0;
-    const u32 tile = take_ticket(ticket, &s_ticket);
-    const u32 base = tile * DB_TILE;
-    dist_stage_tile(text, n, base, sb);
-    __syncthreads();
-    const u32 *sw = reinterpret_cast<const u32 *>(sb);
-    u64 k[DB_ITEMS];
-    u32 keep = 0, cnt = 0;
+    const u32 tpb = (tiles + gridDim.x - 1) / gridDim.x;
+    const u32 t0 = blockIdx.x * tpb, t1 = min(tiles, t0 + tpb);
+    u32 part = 0;
+    for (u32 b = threadIdx.x; b < blockIdx.x; b += DB_BLOCK) part += range_cnt[b];
+    u32 out;
+    block_exclusive_sum(part, s_tmp, &out);               // own rotations of all earlier ranges
+    for (u32 tile = t0; tile < t1; ++tile) {
+        const u32 base = tile * DB_TILE;
+        __syncthreads();
+        dist_stage_tile(text, n, base, sb);
+        __syncthreads();
+        const u32 *sw = reinterpret_cast<const u32 *>(sb);
+        u64 k[DB_ITEMS];
+        u32 keep = 0, cnt = 0;
 #pragma unroll
-    for (int i = 0; i < DB_ITEMS; ++i) {
-        u32 o = threadIdx.x * DB_ITEMS + i;        // blocked: a thread owns consecutive positions, output stays in text order
-        k[i] = dist_window(sw, o);
-        bool own = base + o < n && k[i] >= lo_key && (hi_open || k[i] < hi_key);
-        keep |= (u32)own << i;
-        cnt += own;
-    }
-    u32 total;
-    u32 ex = block_exclusive_sum(cnt, s_tmp, &total);
-    if (threadIdx.x < 32) {
-        u64 x = lookback_exclusive(status, tile, (u64)total, OpSum());
-        if (threadIdx.x == 0) s_base = (u32)x;
-    }
-    __syncthreads();
-    u32 o = s_base + ex;
-#pragma unroll
-    for (int i = 0; i < DB_ITEMS; ++i)
-        if ((keep >> i) & 1u) {
-            keys[o] = k[i];
-            starts[o] = base + threadIdx.x * DB_ITEMS + i;
-            ++o;
-#pragma unroll
-            for (int p = 0; p < 8; ++p) atomicAdd(&s_h[p * 256 + ((u32)(k[i] >> (8 * p)) & 0xffu)], 1u);
+        for (int i = 0; i < DB_ITEMS; ++i) {
+            u32 o = threadIdx.x * DB_ITEMS + i;        // blocked: a thread owns consecutive positions, output stays in text order
+            k[i] = dist_window(sw, o);
+            bool own = base + o < n && k[i] >= lo_key && (hi_open || k[i] < hi_key);
+            keep |= (u32)own << i;
+            cnt += own;
         }
+        u32 total;
+        u32 o = out + block_exclusive_sum(cnt, s_tmp, &total);
+        out += total;
+#pragma unroll
+        for (int i = 0; i < DB_ITEMS; ++i)
+            if ((keep >> i) & 1u) {
+                keys[o] = k[i];
+                starts[o] = base + threadIdx.x * DB_ITEMS + i;
+                ++o;
+#pragma unroll
+                for (int p = 0; p < 8; ++p) atomicAdd(&s_h[p * 256 + ((u32)(k[i] >> (8 * p)) & 0xffu)], 1u);
+            }
+    }
     __syncthreads();
     for (u32 i = threadIdx.x; i < 8 * 256; i += DB_BLOCK) {
         u32 c = s_h[i];
@@ -362,7 +371,36 @@ struct Geometry {
     int owner_of_bucket(u32 b) const { u32 o = b / bpr; return (int)(o < (u32)G ? o : G - 1); }
 };
 
+// BZAP_DIST_TIMING=1: every named phase is bracketed by stream synchronisations and timed on the host
+// (profiling only: the synchronisations cost a little); the table goes to stderr at the end of the call
+struct PhaseTable {
+    bool on = false;
+    cudaStream_t stream = nullptr;
+    const char *names[32];
+    double ms[32];
+    int count = 0;
+    std::chrono::steady_clock::time_point t0;
+    void start() { if (on) { cudaStreamSynchronize(stream); t0 = std::chrono::steady_clock::now(); } }
+    void stop(const char *name)
+    {
+        if (!on) return;
+        cudaStreamSynchronize(stream);
+        double d = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        int i = 0;
+        while (i < count && strcmp(names[i], name) != 0) ++i;
+        if (i == count) { if (count == 32) return; names[count] = name; ms[count] = 0; ++count; }
+        ms[i] += d;
+        t0 = std::chrono::steady_clock::now();
+    }
+    double get(const char *name) const
+    {
+        for (int i = 0; i < count; ++i) if (strcmp(names[i], name) == 0) return ms[i];
+        return 0;
+    }
+};
+
 struct Xchg {
+    PhaseTable pt;
     bzap_ctx *ctx;
     const NcclApi *N;
     ncclComm_t comm;
@@ -414,25 +452,35 @@ static int reduce_words(Xchg &X, const u32 *d_mine, u32 words, u32 *h_local, u32
 }
 
 // all-to-all of variable segments: send holds the segments for ranks 0..G-1 back to back (scnt elements of
-// `es` bytes each), recv receives the segments from ranks 0..G-1 back to back (rcnt)
-static int alltoallv(Xchg &X, const void *send, const u64 *scnt, void *recv, const u64 *rcnt, size_t es)
+// `es` bytes each), recv receives the segments from ranks 0..G-1 back to back (rcnt).  send2 / recv2 (may be
+// null): a second array with the same segmentation, moved in the same NCCL group.
+static int alltoallv(Xchg &X, const void *send, const u64 *scnt, void *recv, const u64 *rcnt, size_t es,
+                     const void *send2 = nullptr, void *recv2 = nullptr)
 {
     bzap_ctx *ctx = X.ctx;
     const int G = X.geo.G, me = X.geo.me;
     u64 soff = 0, roff = 0, my_s = 0, my_r = 0;
     for (int p = 0; p < me; ++p) { my_s += scnt[p]; my_r += rcnt[p]; }
-    if (scnt[me])                                  // own segment: device-to-device copy
+    if (scnt[me]) {                                // own segment: device-to-device copy
         CU(ctx, cudaMemcpyAsync((u8 *)recv + my_r * es, (const u8 *)send + my_s * es, scnt[me] * es, cudaMemcpyDeviceToDevice,
                                 ctx->stream));
+        if (send2)
+            CU(ctx, cudaMemcpyAsync((u8 *)recv2 + my_r * es, (const u8 *)send2 + my_s * es, scnt[me] * es, cudaMemcpyDeviceToDevice,
+                                    ctx->stream));
+    }
     if (G == 1) return BZAP_OK;
     NC(ctx, X.N->GroupStart());
     for (int p = 0; p < G; ++p) {
         if (p != me) {
             if (scnt[p]) {
                 NC(ctx, X.N->Send((const u8 *)send + soff * es, scnt[p] * es, ncclUint8, p, X.comm, ctx->stream));
-                X.sent_bytes += scnt[p] * es;
+                if (send2) NC(ctx, X.N->Send((const u8 *)send2 + soff * es, scnt[p] * es, ncclUint8, p, X.comm, ctx->stream));
+                X.sent_bytes += scnt[p] * es * (send2 ? 2 : 1);
             }
-            if (rcnt[p]) NC(ctx, X.N->Recv((u8 *)recv + roff * es, rcnt[p] * es, ncclUint8, p, X.comm, ctx->stream));
+            if (rcnt[p]) {
+                NC(ctx, X.N->Recv((u8 *)recv + roff * es, rcnt[p] * es, ncclUint8, p, X.comm, ctx->stream));
+                if (recv2) NC(ctx, X.N->Recv((u8 *)recv2 + roff * es, rcnt[p] * es, ncclUint8, p, X.comm, ctx->stream));
+            }
         }
         soff += scnt[p];
         roff += rcnt[p];
@@ -455,6 +503,7 @@ static void counts_from_hists(const Geometry &geo, const u32 *h_all /* [G][256] 
 
 struct HomeBufs {
     u32 *b_idx, *b_val;       // bucketed pairs (capacity: pairs sent)
+    u32 *x_idx, *x_val;       // received pairs regrouped by shard window (capacity: shard)
     u32 *r_idx, *r_val;       // received pairs (capacity: shard)
     u32 *d_hist, *d_bctl;     // 256 words, bucket_ctl_words
 };
@@ -464,35 +513,47 @@ static int ranks_go_home(Xchg &X, const u32 *d_idx, const u32 *d_val, u32 cnt, c
 {
     bzap_ctx *ctx = X.ctx;
     const Geometry &geo = X.geo;
+    X.pt.start();
+    const u32 *s_idx = B.b_idx, *s_val = B.b_val;                // what is sent: pairs grouped by owner
     if (cnt) RET(dev_bucket_pass_u32(ctx, d_idx, d_val, cnt, (int)geo.shift, B.b_idx, B.b_val, B.d_hist, B.d_bctl));
     else CU(ctx, cudaMemsetAsync(B.d_hist, 0, 256 * sizeof(u32), ctx->stream));
+    X.pt.stop("home.bucket");
     u32 *h_all = nullptr;
     RET(gather_words(X, B.d_hist, 256, &h_all));
+    X.pt.stop("home.counts");
     u64 scnt[DIST_MAX_WORLD], rcnt[DIST_MAX_WORLD], total = 0;
     counts_from_hists(geo, h_all, scnt, rcnt);
     for (int s = 0; s < geo.G; ++s) total += rcnt[s];
     if (total > (u64)(geo.hi(geo.me) - geo.lo(geo.me))) return bzap_fail(ctx, BZAP_ERR_CUDA, "ranks_go_home: %llu pairs for a shard of %u",
                                                                           (unsigned long long)total, geo.hi(geo.me) - geo.lo(geo.me));
-    RET(alltoallv(X, B.b_idx, scnt, B.r_idx, rcnt, sizeof(u32)));
-    RET(alltoallv(X, B.b_val, scnt, B.r_val, rcnt, sizeof(u32)));
-    RET(dev_scatter_offset_async(ctx, B.r_idx, B.r_val, (u32)total, geo.lo(geo.me), rank_home));
+    RET(alltoallv(X, s_idx, scnt, B.r_idx, rcnt, sizeof(u32), s_val, B.r_val));
+    X.pt.stop("home.alltoall");
+    // The pairs arrive as one run per sender.  Scattered as they are, every 32-byte sector of the shard
+    // would be touched once per sender, far apart in time, and be read-modified-written each time (measured
+    // at 4 GPUs: 31 G pairs/s against 112 G/s for one sender).  So the owner regroups what it received by
+    // the top bits of the shard offset first: all contributions to a window of <= 2^20 entries (4 MiB) sit
+    // together and every sector is completed in L2.  (idx >> s) & 255 is injective over the shard because
+    // the shard starts at a multiple of 2^shift >= 2^s and spans at most 256 windows.
+    const u32 *x_idx = B.r_idx, *x_val = B.r_val;
+    if (total > (4u << 20)) {
+        u32 lbits = 0;
+        while (((u64)1 << lbits) < (u64)(geo.hi(geo.me) - geo.lo(geo.me))) ++lbits;
+        if (lbits > 28) {                                             // two LSD passes: windows of 2^(lbits-16) entries
+            RET(dev_bucket_pass_u32(ctx, B.r_idx, B.r_val, (u32)total, (int)lbits - 16, B.x_idx, B.x_val, B.d_hist, B.d_bctl));
+            RET(dev_bucket_pass_u32(ctx, B.x_idx, B.x_val, (u32)total, (int)lbits - 8, B.r_idx, B.r_val, B.d_hist, B.d_bctl));
+        } else if (lbits > 20) {
+            RET(dev_bucket_pass_u32(ctx, B.r_idx, B.r_val, (u32)total, (int)lbits - 8, B.x_idx, B.x_val, B.d_hist, B.d_bctl));
+            x_idx = B.x_idx;
+            x_val = B.x_val;
+        }
+    }
+    X.pt.stop("home.regroup");
+    RET(dev_scatter_offset_async(ctx, x_idx, x_val, (u32)total, geo.lo(geo.me), rank_home));
+    X.pt.stop("home.scatter");
     CU(ctx, cudaGetLastError());
     return BZAP_OK;
 }
 
-struct PhaseClock {
-    bzap_ctx *ctx;
-    bool on;
-    std::chrono::steady_clock::time_point t0;
-    void start() { if (on) { cudaStreamSynchronize(ctx->stream); t0 = std::chrono::steady_clock::now(); } }
-    void stop(double *acc)
-    {
-        if (on) {
-            cudaStreamSynchronize(ctx->stream);
-            *acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        }
-    }
-};
 static double ev_ms2(cudaEvent_t a, cudaEvent_t b)
 {
     float ms = 0;
@@ -521,9 +582,10 @@ extern "C" int bzap_compress_block_distributed(bzap_ctx *ctx, const uint8_t *d_t
     st = bzap_dist_stats{};
     st.world = G;
     st.rank = me;
-    PhaseClock clk{ctx, getenv("BZAP_DIST_TIMING") != nullptr, {}};
-
     Xchg X;
+    X.pt.on = getenv("BZAP_DIST_TIMING") != nullptr;
+    X.pt.stream = ctx->stream;
+    PhaseTable &pt = X.pt;
     X.ctx = ctx;
     X.N = N;
     X.comm = (ncclComm_t)ctx->comm;
@@ -565,13 +627,19 @@ extern "C" int bzap_compress_block_distributed(bzap_ctx *ctx, const uint8_t *d_t
     if (!d_cnt) return bzap_fail(ctx, BZAP_ERR_NOMEM, "count scratch");
     CU(ctx, cudaMemsetAsync(d_cnt, 0, 8 * sizeof(u32), ctx->stream));
     const u32 text_tiles = (n + DB_TILE - 1) / DB_TILE;
+    const u32 sel_grid = grid_1d(text_tiles, 1, 148 * 8);
     u32 base = 0, m = n;
-    if (G > 1) {
-        LAUNCH(ctx, dist_owner_count_kernel, grid_1d(text_tiles, 1, 148 * 8), DB_BLOCK, 0, d_text, n, bound_lo, bound_hi, hi_open, d_cnt);
+    std::vector<u32> range_cnt(sel_grid);
+    {
+        u32 *d_rc = arena_get<u32>(ctx, sel_grid);
+        if (!d_rc || (size_t)sel_grid * 4 + 64 > DIST_HOST_BYTES) return bzap_fail(ctx, BZAP_ERR_NOMEM, "count scratch");
+        LAUNCH(ctx, dist_owner_count_kernel, sel_grid, DB_BLOCK, 0, d_text, n, bound_lo, bound_hi, hi_open, text_tiles, d_cnt, d_rc);
         CU(ctx, cudaMemcpyAsync(ctx->dist_host, d_cnt, 2 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(ctx->dist_host + 64, d_rc, (size_t)sel_grid * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaStreamSynchronize(ctx->stream));
         base = ((u32 *)ctx->dist_host)[0];
         m = ((u32 *)ctx->dist_host)[1];
+        memcpy(range_cnt.data(), ctx->dist_host + 64, (size_t)sel_grid * 4);
     }
     st.own_rotations = m;
 
@@ -581,7 +649,7 @@ extern "C" int bzap_compress_block_distributed(bzap_ctx *ctx, const uint8_t *d_t
                              (148 * 6 + 8) + 4096;
     const size_t need = 16 * mm + 8 * mm /* sort keys, payloads */ + 4 * mm /* rs */ + 12 * mm /* V1..V3 */ +
                         16 * mm /* act_r1 next_r1 newr pos */ + 4 * mm /* r2 */ + 4 * sh /* rank_home */ + 8 * sh /* requests in */ +
-                        4 * sh /* responses out */ + 8 * sh /* pairs in */ + ctl_words * 4 + active_ctl_bytes(m, nullptr, nullptr) +
+                        4 * sh /* responses out */ + 16 * sh /* pairs in, regrouped */ + ctl_words * 4 + active_ctl_bytes(m, nullptr, nullptr) +
                         sort_scratch_bytes(m) + 4 * (mm + 1024) /* last column, mtf, piece */ +
                         (me == 0 ? 2 * bzap_compress_bound(n) : 0) /* file image, staged pieces */ + mtf_scratch_bytes(m) +
                         (size_t)m / 16 + (16u << 20);
@@ -597,18 +665,19 @@ extern "C" int bzap_compress_block_distributed(bzap_ctx *ctx, const uint8_t *d_t
     u64 *req_in = arena_get<u64>(ctx, sh);
     u32 *resp_out = arena_get<u32>(ctx, sh);
     u32 *home_idx = arena_get<u32>(ctx, sh), *home_val = arena_get<u32>(ctx, sh);
+    u32 *home_xi = arena_get<u32>(ctx, sh), *home_xv = arena_get<u32>(ctx, sh);
     u32 *d_hist8 = arena_get<u32>(ctx, 8 * 256 + 64);
     u32 *d_rrctl = arena_get<u32>(ctx, rerank_ctl_words(m));
     u32 *d_bctl = arena_get<u32>(ctx, bucket_ctl_words(m > shard ? m : shard));
     u32 *d_h256 = arena_get<u32>(ctx, 1024);
     X.d_small = arena_get<u32>(ctx, (size_t)G * 1024);
     u32 *d_bact = arena_get<u32>(ctx, 148 * 6 + 8);
-    u64 *d_selstatus = arena_get<u64>(ctx, (size_t)text_tiles + 8);
+    u32 *d_range_cnt = arena_get<u32>(ctx, sel_grid + 8);
     u8 *d_actctl = arena_get<u8>(ctx, active_ctl_bytes(m, nullptr, nullptr));
     d_cnt = arena_get<u32>(ctx, 16);
     if (!K0 || !K1 || !SV0 || !SV1 || !d_rs || !V1 || !V2 || !V3 || !act_r1 || !next_r1 || !newr || !posb || !d_r2 || !rank_home ||
-        !req_in || !resp_out || !home_idx || !home_val || !d_hist8 || !d_rrctl || !d_bctl || !d_h256 || !X.d_small || !d_bact ||
-        !d_selstatus || !d_actctl || !d_cnt)
+        !req_in || !resp_out || !home_idx || !home_val || !home_xi || !home_xv || !d_hist8 || !d_rrctl || !d_bctl || !d_h256 || !X.d_small || !d_bact ||
+        !d_range_cnt || !d_actctl || !d_cnt)
         return bzap_fail(ctx, BZAP_ERR_NOMEM, "distributed block scratch");
     const size_t arena_mark = ctx->arena_off;
 
@@ -616,17 +685,21 @@ extern "C" int bzap_compress_block_distributed(bzap_ctx *ctx, const uint8_t *d_t
     u64 *keys = nullptr;
     u32 *sa = nullptr;
     CU(ctx, cudaMemsetAsync(d_hist8, 0, (8 * 256 + 64) * sizeof(u32), ctx->stream));
-    CU(ctx, cudaMemsetAsync(d_selstatus, 0, ((size_t)text_tiles + 8) * sizeof(u64), ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_range_cnt, range_cnt.data(), (size_t)sel_grid * 4, cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx, cudaMemsetAsync(d_rrctl, 0, rerank_ctl_words(m) * sizeof(u32), ctx->stream));
+    pt.start();
     if (m) {
-        LAUNCH(ctx, dist_select_kernel, text_tiles, DB_BLOCK, 0, d_text, n, bound_lo, bound_hi, hi_open, K0, SV0, d_hist8,
-               d_selstatus, d_hist8 + 8 * 256);
+        LAUNCH(ctx, dist_select_kernel, sel_grid, DB_BLOCK, 0, d_text, n, bound_lo, bound_hi, hi_open, text_tiles, d_range_cnt, K0, SV0,
+               d_hist8);
+        pt.stop("first.select");
         SortBuffers sb;
         sb.keys[0] = K0; sb.keys[1] = K1; sb.vals[0] = SV0; sb.vals[1] = SV1;
         int passes = 0;
         RET(dev_sort_pairs64(ctx, &sb, m, 0xffu, d_hist8, 8, false, &keys, &sa, &passes));
         ctx->arena_off = arena_mark;
+        pt.stop("first.sort");
         RET(dev_rerank_sorted(ctx, keys, m, base, d_rs, d_rrctl, d_bact));
+        pt.stop("first.rerank");
     } else {
         sa = SV0;
     }
@@ -635,7 +708,7 @@ extern "C" int bzap_compress_block_distributed(bzap_ctx *ctx, const uint8_t *d_t
 
     // ---- 2. ranks go home ------------------------------------------------------------------------------------------
     HomeBufs HB;
-    HB.r_idx = home_idx; HB.r_val = home_val; HB.d_hist = d_h256; HB.d_bctl = d_bctl;
+    HB.r_idx = home_idx; HB.r_val = home_val; HB.x_idx = home_xi; HB.x_val = home_xv; HB.d_hist = d_h256; HB.d_bctl = d_bctl;
     HB.b_idx = V1; HB.b_val = V2;
     RET(ranks_go_home(X, sa, d_rs, m, HB, rank_home));
     CU(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -648,7 +721,9 @@ extern "C" int bzap_compress_block_distributed(bzap_ctx *ctx, const uint8_t *d_t
     RET(reduce_words(X, d_cnt, 4, h_loc, h_sum));
     u32 M = m - h_loc[1];
     u64 total_active = (u64)n - h_sum[1];            // every rotation is owned by exactly one rank
+    pt.start();
     if (M) RET(dev_collect_active(ctx, d_rs, sa, m, base, d_bact, V0, act_r1));
+    pt.stop("first.collect");
     ActiveWork w;
     active_ctl_bytes(m, &w, d_actctl);
     w.newr = newr;
@@ -665,30 +740,34 @@ extern "C" int bzap_compress_block_distributed(bzap_ctx *ctx, const uint8_t *d_t
         CU(ctx, cudaMemsetAsync(w.zero_base, 0, w.zero_bytes, ctx->stream));
         CU(ctx, cudaMemsetAsync(d_h256, 0, 256 * sizeof(u32), ctx->stream));
         // pull r2 = rank[(start + k) mod n]
-        clk.start();
+        pt.start();
         if (M) {
             LAUNCH(ctx, dist_request_kernel, grid_1d(M, 256 * 4), 256, 0, act_idx, act_r1, M, n, kk, geo.shift, K0, d_h256);
             if (G > 1) RET(dev_bucket_pass_u64(ctx, K0, act_idx, M, 32 + (int)geo.shift, K1, V1, d_h256, d_bctl));
         }
+        pt.stop("pull.request+bucket");
         u64 *bk = G > 1 ? K1 : K0;                   // requests grouped by owner (one owner: nothing to regroup)
         u32 *bidx = G > 1 ? V1 : act_idx;
         u64 scnt[DIST_MAX_WORLD] = {M}, rcnt[DIST_MAX_WORLD] = {M}, total_req = M;
         if (G > 1) {
             u32 *h_all = nullptr;
             RET(gather_words(X, d_h256, 256, &h_all));
+            pt.stop("pull.counts");
             counts_from_hists(geo, h_all, scnt, rcnt);
             total_req = 0;
             for (int s = 0; s < G; ++s) total_req += rcnt[s];
             if (total_req > shard) return bzap_fail(ctx, BZAP_ERR_CUDA, "pull: %llu requests for a shard of %u", (unsigned long long)total_req, shard);
             RET(alltoallv(X, bk, scnt, req_in, rcnt, sizeof(u64)));
+            pt.stop("pull.alltoall requests");
             if (total_req) LAUNCH(ctx, dist_respond_kernel, grid_1d(total_req, 256 * 4), 256, 0, req_in, (u32)total_req, rank_home, lo, resp_out);
+            pt.stop("pull.respond");
             RET(alltoallv(X, resp_out, rcnt, d_r2, scnt, sizeof(u32)));
+            pt.stop("pull.alltoall responses");
         } else if (M) {
             LAUNCH(ctx, dist_respond_kernel, grid_1d(M, 256 * 4), 256, 0, bk, M, rank_home, lo, d_r2);
+            pt.stop("pull.respond");
         }
-        clk.stop(&st.ms_pull);
         // local sort by (r1, r2), new sparse ranks inside every group's slot range, survivors
-        clk.start();
         u64 *skeys = nullptr;
         u32 *sidx = nullptr;
         if (M) {
@@ -701,16 +780,16 @@ extern "C" int bzap_compress_block_distributed(bzap_ctx *ctx, const uint8_t *d_t
             RET(bwt_active_sort_rerank(ctx, w, &ab, M, rshift, pair_mask, base, nullptr, next_idx, next_r1, &skeys, &sidx, &passes));
             ctx->arena_off = arena_mark;
         }
-        clk.stop(&st.ms_round_sort);
+        pt.stop("round.sort+rerank");
         // new ranks go home (all of this round's rotations: the unchanged ones are rewritten with the same value)
-        clk.start();
         HB.b_idx = G > 1 ? act_idx : V1;             // dead buffers of this round
         HB.b_val = posb;
         RET(ranks_go_home(X, sidx, newr, M, HB, rank_home));
-        clk.stop(&st.ms_home);
         ++rounds;
         k *= 2;
+        pt.start();
         RET(reduce_words(X, w.d_counters, 4, h_loc, h_sum));
+        pt.stop("round.termination");
         const u64 groups = h_sum[0], subs = h_sum[1];
         total_active = h_sum[2];
         M = h_loc[2];
@@ -726,7 +805,9 @@ extern "C" int bzap_compress_block_distributed(bzap_ctx *ctx, const uint8_t *d_t
     u64 *d_stat = arena_get<u64>(ctx, 256 + 128 + 8);
     u32 *d_init = arena_get<u32>(ctx, 256);
     if (!d_last || !d_mtf || !d_stat || !d_init) return bzap_fail(ctx, BZAP_ERR_NOMEM, "tail scratch");
+    pt.start();
     if (m) RET(dev_gather_slots(ctx, d_text, sa, n, m, d_last));
+    pt.stop("tail.last column");
     u64 primary = 0;
     {
         u32 *d_p = d_cnt + 8;
@@ -766,6 +847,7 @@ extern "C" int bzap_compress_block_distributed(bzap_ctx *ctx, const uint8_t *d_t
         }
     }
     RET(dev_mtf_finish(ctx, d_last, &plan, d_init_use, d_mtf));
+    pt.stop("tail.mtf");
 
     // ---- 6. Huffman: global statistics, the tree everywhere, pieces at their bit offsets ------------------------------
     RET(dev_hist_launch(ctx, d_mtf, m, d_stat));
@@ -852,13 +934,21 @@ extern "C" int bzap_compress_block_distributed(bzap_ctx *ctx, const uint8_t *d_t
             X.sent_bytes += pb;
         }
     }
+    pt.stop("tail.huffman+gather");
     CU(ctx, cudaEventRecord(ctx->ev[7], ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaGetLastError());
     st.exchanged_bytes = X.sent_bytes;
     st.ms_total = ev_ms2(ctx->ev[0], ctx->ev[7]);
     st.ms_select_sort = ev_ms2(ctx->ev[0], ctx->ev[1]);
-    if (!clk.on) st.ms_home = ev_ms2(ctx->ev[1], ctx->ev[2]);
+    st.ms_home = ev_ms2(ctx->ev[1], ctx->ev[2]);
+    st.ms_pull = pt.get("pull.request+bucket") + pt.get("pull.counts") + pt.get("pull.alltoall requests") + pt.get("pull.respond") +
+                 pt.get("pull.alltoall responses");
+    st.ms_round_sort = pt.get("round.sort+rerank");
+    if (pt.on && me == 0) {
+        fprintf(stderr, "[bzap dist] world %d n %u rounds %u total %.2f ms (with profiling synchronisations)\n", G, n, rounds, st.ms_total);
+        for (int i = 0; i < pt.count; ++i) fprintf(stderr, "[bzap dist]   %-28s %9.2f ms\n", pt.names[i], pt.ms[i]);
+    }
     st.ms_rounds = ev_ms2(ctx->ev[2], ctx->ev[3]);
     st.ms_tail = ev_ms2(ctx->ev[3], ctx->ev[7]);
     ctx->stats.bwt_rounds = rounds;

@@ -10,10 +10,10 @@ One BWT block = whole input (main.cpp:77-91, README.md:40).  The text is replica
                     rank g owns the rotations whose 8-byte key lies in [spl[g], spl[g+1]): equal keys
                     never straddle two ranks, so groups and their sparse ranks are local for ever
   1. select + sort  own (key, start) pairs, local sort, sparse ranks rs = base_g + group head
-  2. ranks go home  (start, rank) to the owner of text position `start` (contiguous shards)
+  2. ranks go home  (start, rank) to the owner of text position `start` (contiguous shards, bucket aligned)
   3. rounds         active = rotations in a group > 1: pull r2 = rank[(start + k) mod N] from the
                     position owners (request / response all-to-all), sort (r1, r2) locally, new
-                    sparse ranks inside the group's slot range, changed ranks go home, survivors stay
+                    sparse ranks inside the group's slot range, ranks go home, survivors stay
   4. last column    L[j] = text[(sa[j] - 1) mod N] per rank; primary = rank[0]
   5. MTF            per-rank "last occurrence" summary, all-gather, start list of every rank
   6. Huffman        per-rank histogram + first appearance, all-gather; tree on every rank; per-rank
@@ -81,7 +81,12 @@ def splitters(text, world):
 
 
 def shard_len(n, world):
-    return -(-n // world)
+    """Contiguous shards of text positions, aligned to the 256 top-bit buckets the exchange regroups by
+    (Geometry in dist_block.cu): bucket = position >> shift, ceil(buckets / world) buckets per rank."""
+    bits = max(int(n - 1).bit_length(), 0) if n > 1 else 0
+    shift = max(bits - 8, 0)
+    nb = -(-n // (1 << shift))
+    return (-(-nb // world)) << shift
 
 
 # ---- MTF pieces -------------------------------------------------------------------------------------------
@@ -192,8 +197,7 @@ def compress_block_distributed(text, group=None, stats=None):
         sh[1:] |= s_r2[1:] != s_r2[:-1]
         newr = np.maximum.accumulate(np.where(sh, slot, 0)) if m else np.zeros(0, np.int64)
         sa[slot - base] = s_idx
-        changed = newr != s_r1
-        go_home(s_idx[changed], newr[changed])
+        go_home(s_idx, newr)                                 # unchanged ranks are rewritten with the same value
         ssingle = sh & np.append(sh[1:], True) if m else np.zeros(0, bool)
         keep = ~ssingle
         act_idx, act_r1 = s_idx[keep], newr[keep]

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-calgary > gpurun_out/plain.log 2>&1 &&
+python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-block1g --no-calgary > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-calgary > gpurun_out/ncu.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-block1g --no-calgary > gpurun_out/ncu.log 2>&1
 echo "launch list rc=$?"
