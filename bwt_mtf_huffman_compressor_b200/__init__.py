@@ -59,7 +59,7 @@ class Stats(C.Structure):
 
 class DistStats(C.Structure):
     """bzap_dist_stats of include/bzap.h."""
-    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("rounds", C.c_uint32), ("reserved", C.c_uint32),
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("rounds", C.c_uint32), ("peer_windows", C.c_uint32),
                 ("own_rotations", C.c_uint64), ("exchanged_bytes", C.c_uint64), ("ms_total", C.c_double),
                 ("ms_select_sort", C.c_double), ("ms_home", C.c_double), ("ms_rounds", C.c_double), ("ms_pull", C.c_double),
                 ("ms_round_sort", C.c_double), ("ms_tail", C.c_double)]

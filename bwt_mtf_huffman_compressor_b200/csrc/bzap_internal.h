@@ -33,6 +33,7 @@ struct bzap_ctx {
     void *comm = nullptr;               // ncclComm_t
     int world = 1, rank = 0;
     u8 *dist_host = nullptr;            // pinned staging for the small collectives
+    void *peers = nullptr;              // the other ranks' arenas mapped through CUDA IPC (dist_block.cu: PeerMap)
     bzap_dist_stats dstats = {};
     char err[256] = {0};
 };

@@ -115,8 +115,28 @@ extern "C" int bzap_comm_unique_id(uint8_t id[BZAP_COMM_ID_BYTES])
     return BZAP_OK;
 }
 
+// Peer windows: every rank's scratch arena (one cudaMalloc) is mapped into the other ranks' address spaces
+// through CUDA IPC, so that the bulk exchanges are plain device-to-device copies over NVLink into the
+// receiver's buffer (measured on this pool: 760 GB/s per copy against 150-270 GB/s for the same segments
+// through ncclSend/ncclRecv groups).  NCCL keeps the small collectives, which double as the barriers.
+struct PeerMap {
+    cudaIpcMemHandle_t handle[DIST_MAX_WORLD];
+    u8 *base[DIST_MAX_WORLD];
+    bool open[DIST_MAX_WORLD];
+};
+static void peers_close(bzap_ctx *ctx)
+{
+    PeerMap *pm = (PeerMap *)ctx->peers;
+    if (!pm) return;
+    for (int p = 0; p < DIST_MAX_WORLD; ++p)
+        if (pm->open[p]) cudaIpcCloseMemHandle(pm->base[p]);
+    delete pm;
+    ctx->peers = nullptr;
+}
+
 void dist_comm_release(bzap_ctx *ctx)
 {
+    peers_close(ctx);
     if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)ctx->comm);
     ctx->comm = nullptr;
     ctx->world = 1;
@@ -408,6 +428,15 @@ struct Xchg {
     u32 *d_small;     // device scratch for the small collectives: G x 1024 words
     u8 *h;            // pinned host, DIST_HOST_BYTES
     u64 sent_bytes = 0;
+    // peer windows (see PeerMap): base of every rank's arena in this address space, and the offsets of
+    // the buffers that peers push into
+    bool p2p = false;
+    u8 *peer_base[DIST_MAX_WORLD] = {};
+    u64 peer_off[DIST_MAX_WORLD][4] = {};
+};
+enum { BUF_HOME_IDX = 0, BUF_HOME_VAL = 1, BUF_REQ_IN = 2, BUF_R2 = 3 };
+struct CountMatrix {
+    u64 c[DIST_MAX_WORLD][DIST_MAX_WORLD];       // c[s][d] = elements rank s holds for rank d
 };
 
 static inline u32 grid_1d(u64 items, u32 per_block, u32 cap = 148u * 8u)
@@ -451,54 +480,154 @@ static int reduce_words(Xchg &X, const u32 *d_mine, u32 words, u32 *h_local, u32
     return BZAP_OK;
 }
 
-// all-to-all of variable segments: send holds the segments for ranks 0..G-1 back to back (scnt elements of
-// `es` bytes each), recv receives the segments from ranks 0..G-1 back to back (rcnt).  send2 / recv2 (may be
-// null): a second array with the same segmentation, moved in the same NCCL group.
-static int alltoallv(Xchg &X, const void *send, const u64 *scnt, void *recv, const u64 *rcnt, size_t es,
-                     const void *send2 = nullptr, void *recv2 = nullptr)
+// all-to-all of variable segments: send holds the segments for ranks 0..G-1 back to back, recv receives the
+// segments from ranks 0..G-1 back to back; C (read transposed when `back`: an answer travels the way its
+// request came) says how many elements of `es` bytes everybody holds for everybody.  send2 / recv2 (may be
+// null): a second array with the same segmentation.  `buf` / `buf2` name the receiving buffers in the
+// peers' arenas.  With peer windows the segments are copied straight into the receivers' buffers and a
+// one-word all-reduce tells everybody that all copies have landed; otherwise one ncclSend/ncclRecv group.
+static int alltoallv(Xchg &X, const void *send, void *recv, size_t es, const CountMatrix &C, bool back, int buf,
+                     const void *send2 = nullptr, void *recv2 = nullptr, int buf2 = 0)
 {
     bzap_ctx *ctx = X.ctx;
     const int G = X.geo.G, me = X.geo.me;
-    u64 soff = 0, roff = 0, my_s = 0, my_r = 0;
-    for (int p = 0; p < me; ++p) { my_s += scnt[p]; my_r += rcnt[p]; }
-    if (scnt[me]) {                                // own segment: device-to-device copy
-        CU(ctx, cudaMemcpyAsync((u8 *)recv + my_r * es, (const u8 *)send + my_s * es, scnt[me] * es, cudaMemcpyDeviceToDevice,
+    auto cnt = [&](int s_, int d_) { return back ? C.c[d_][s_] : C.c[s_][d_]; };
+    u64 my_s = 0, my_r = 0;
+    for (int p = 0; p < me; ++p) { my_s += cnt(me, p); my_r += cnt(p, me); }
+    if (cnt(me, me)) {                             // own segment
+        CU(ctx, cudaMemcpyAsync((u8 *)recv + my_r * es, (const u8 *)send + my_s * es, cnt(me, me) * es, cudaMemcpyDeviceToDevice,
                                 ctx->stream));
         if (send2)
-            CU(ctx, cudaMemcpyAsync((u8 *)recv2 + my_r * es, (const u8 *)send2 + my_s * es, scnt[me] * es, cudaMemcpyDeviceToDevice,
-                                    ctx->stream));
+            CU(ctx, cudaMemcpyAsync((u8 *)recv2 + my_r * es, (const u8 *)send2 + my_s * es, cnt(me, me) * es,
+                                    cudaMemcpyDeviceToDevice, ctx->stream));
     }
     if (G == 1) return BZAP_OK;
+    if (X.p2p) {
+        u64 soffs[DIST_MAX_WORLD], run = 0;
+        for (int p = 0; p < G; ++p) { soffs[p] = run; run += cnt(me, p); }
+        // destinations in the order me+1, me+2, ...: at every step each GPU is written by one sender only
+        // (everybody starting with rank 0 would make the receiver's NVLink ingress the bottleneck)
+        for (int i = 1; i < G; ++i) {
+            const int p = (me + i) % G;
+            const u64 c = cnt(me, p);
+            if (!c) continue;
+            u64 dst = 0;                           // where my segment starts in p's buffer: after the lower ranks' segments
+            for (int s_ = 0; s_ < me; ++s_) dst += cnt(s_, p);
+            CU(ctx, cudaMemcpyAsync(X.peer_base[p] + X.peer_off[p][buf] + dst * es, (const u8 *)send + soffs[p] * es, c * es,
+                                    cudaMemcpyDefault, ctx->stream));
+            if (send2)
+                CU(ctx, cudaMemcpyAsync(X.peer_base[p] + X.peer_off[p][buf2] + dst * es, (const u8 *)send2 + soffs[p] * es, c * es,
+                                        cudaMemcpyDefault, ctx->stream));
+            X.sent_bytes += c * es * (send2 ? 2 : 1);
+        }
+        // every rank's copies precede its contribution in stream order: when the reduction completes here,
+        // all segments addressed to this rank have landed
+        u32 *d_flag = X.d_small + (size_t)G * 1024 - 8;
+        NC(ctx, X.N->AllReduce(d_flag, d_flag + 4, 1, ncclUint32, ncclSum, X.comm, ctx->stream));
+        return BZAP_OK;
+    }
+    u64 soff = 0, roff = 0;
     NC(ctx, X.N->GroupStart());
     for (int p = 0; p < G; ++p) {
+        const u64 sc = cnt(me, p), rc = cnt(p, me);
         if (p != me) {
-            if (scnt[p]) {
-                NC(ctx, X.N->Send((const u8 *)send + soff * es, scnt[p] * es, ncclUint8, p, X.comm, ctx->stream));
-                if (send2) NC(ctx, X.N->Send((const u8 *)send2 + soff * es, scnt[p] * es, ncclUint8, p, X.comm, ctx->stream));
-                X.sent_bytes += scnt[p] * es * (send2 ? 2 : 1);
+            if (sc) {
+                NC(ctx, X.N->Send((const u8 *)send + soff * es, sc * es, ncclUint8, p, X.comm, ctx->stream));
+                if (send2) NC(ctx, X.N->Send((const u8 *)send2 + soff * es, sc * es, ncclUint8, p, X.comm, ctx->stream));
+                X.sent_bytes += sc * es * (send2 ? 2 : 1);
             }
-            if (rcnt[p]) {
-                NC(ctx, X.N->Recv((u8 *)recv + roff * es, rcnt[p] * es, ncclUint8, p, X.comm, ctx->stream));
-                if (recv2) NC(ctx, X.N->Recv((u8 *)recv2 + roff * es, rcnt[p] * es, ncclUint8, p, X.comm, ctx->stream));
+            if (rc) {
+                NC(ctx, X.N->Recv((u8 *)recv + roff * es, rc * es, ncclUint8, p, X.comm, ctx->stream));
+                if (recv2) NC(ctx, X.N->Recv((u8 *)recv2 + roff * es, rc * es, ncclUint8, p, X.comm, ctx->stream));
             }
         }
-        soff += scnt[p];
-        roff += rcnt[p];
+        soff += sc;
+        roff += rc;
     }
     NC(ctx, X.N->GroupEnd());
     return BZAP_OK;
 }
 
-// per-destination counts of this rank and per-source counts for this rank from everybody's bucket histograms
-static void counts_from_hists(const Geometry &geo, const u32 *h_all /* [G][256] */, u64 *scnt, u64 *rcnt)
+// who holds how much for whom, from everybody's bucket histograms (whole buckets belong to one owner)
+static void matrix_from_hists(const Geometry &geo, const u32 *h_all /* [G][256] */, CountMatrix *C)
 {
-    for (int p = 0; p < geo.G; ++p) scnt[p] = rcnt[p] = 0;
-    for (u32 b = 0; b < 256; ++b) {
-        const int o = geo.owner_of_bucket(b);
-        scnt[o] += h_all[(size_t)geo.me * 256 + b];
-        if (o == geo.me)
-            for (int s = 0; s < geo.G; ++s) rcnt[s] += h_all[(size_t)s * 256 + b];
+    for (int s = 0; s < geo.G; ++s) {
+        for (int d = 0; d < geo.G; ++d) C->c[s][d] = 0;
+        for (u32 b = 0; b < 256; ++b) C->c[s][geo.owner_of_bucket(b)] += h_all[(size_t)s * 256 + b];
     }
+}
+
+// maps the peers' arenas (or learns that it cannot): collective.  offs = offsets of this rank's receiving
+// buffers inside its arena
+static int peers_setup(Xchg &X, const u64 offs[4])
+{
+    bzap_ctx *ctx = X.ctx;
+    const int G = X.geo.G, me = X.geo.me;
+    X.p2p = false;
+    if (G == 1) return BZAP_OK;
+    const bool want = getenv("BZAP_DIST_NO_P2P") == nullptr;
+    struct Hello {
+        cudaIpcMemHandle_t handle;
+        u64 off[4];
+        u32 ok, pad[7];
+    };
+    static_assert(sizeof(Hello) % 4 == 0 && sizeof(Hello) / 4 <= 64, "hello size");
+    const u32 words = sizeof(Hello) / 4;
+    Hello mine;
+    memset(&mine, 0, sizeof mine);
+    mine.ok = want && cudaIpcGetMemHandle(&mine.handle, ctx->arena) == cudaSuccess;
+    if (!mine.ok) cudaGetLastError();
+    for (int i = 0; i < 4; ++i) mine.off[i] = offs[i];
+    u32 *d_mine = X.d_small + (size_t)G * 1024 - 128;
+    u8 *h_stage = X.h + DIST_HOST_BYTES - 1024;
+    memcpy(h_stage, &mine, sizeof mine);
+    CU(ctx, cudaMemcpyAsync(d_mine, h_stage, sizeof mine, cudaMemcpyHostToDevice, ctx->stream));
+    u32 *h_all = nullptr;
+    RET(gather_words(X, d_mine, words, &h_all));
+    if (!ctx->peers) {
+        PeerMap *pm = new (std::nothrow) PeerMap();
+        if (!pm) return bzap_fail(ctx, BZAP_ERR_NOMEM, "peer map");
+        memset(pm, 0, sizeof *pm);
+        ctx->peers = pm;
+    }
+    PeerMap *pm = (PeerMap *)ctx->peers;
+    u32 all_ok = 1;
+    std::vector<Hello> hello(G);
+    for (int p = 0; p < G; ++p) {
+        memcpy(&hello[p], h_all + (size_t)p * words, sizeof(Hello));
+        all_ok &= hello[p].ok;
+    }
+    u32 my_ok = all_ok;
+    if (all_ok) {
+        for (int p = 0; p < G && my_ok; ++p) {
+            if (p == me) continue;
+            if (pm->open[p] && memcmp(&pm->handle[p], &hello[p].handle, sizeof(cudaIpcMemHandle_t)) == 0) continue;
+            if (pm->open[p]) { cudaIpcCloseMemHandle(pm->base[p]); pm->open[p] = false; }
+            void *b = nullptr;
+            if (cudaIpcOpenMemHandle(&b, hello[p].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                my_ok = 0;
+                break;
+            }
+            pm->base[p] = (u8 *)b;
+            pm->handle[p] = hello[p].handle;
+            pm->open[p] = true;
+        }
+    }
+    // everybody must have mapped everybody, or nobody uses the windows
+    u32 *h_ok = (u32 *)h_stage;
+    *h_ok = my_ok;
+    CU(ctx, cudaMemcpyAsync(d_mine, h_ok, sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+    RET(gather_words(X, d_mine, 1, &h_all));
+    bool ok = true;
+    for (int p = 0; p < G; ++p) ok = ok && h_all[p] != 0;
+    if (ok)
+        for (int p = 0; p < G; ++p) {
+            X.peer_base[p] = p == me ? ctx->arena : pm->base[p];
+            for (int i = 0; i < 4; ++i) X.peer_off[p][i] = hello[p].off[i];
+        }
+    X.p2p = ok;
+    return BZAP_OK;
 }
 
 struct HomeBufs {
@@ -521,12 +650,13 @@ static int ranks_go_home(Xchg &X, const u32 *d_idx, const u32 *d_val, u32 cnt, c
     u32 *h_all = nullptr;
     RET(gather_words(X, B.d_hist, 256, &h_all));
     X.pt.stop("home.counts");
-    u64 scnt[DIST_MAX_WORLD], rcnt[DIST_MAX_WORLD], total = 0;
-    counts_from_hists(geo, h_all, scnt, rcnt);
-    for (int s = 0; s < geo.G; ++s) total += rcnt[s];
+    CountMatrix C;
+    matrix_from_hists(geo, h_all, &C);
+    u64 total = 0;
+    for (int s = 0; s < geo.G; ++s) total += C.c[s][geo.me];
     if (total > (u64)(geo.hi(geo.me) - geo.lo(geo.me))) return bzap_fail(ctx, BZAP_ERR_CUDA, "ranks_go_home: %llu pairs for a shard of %u",
                                                                           (unsigned long long)total, geo.hi(geo.me) - geo.lo(geo.me));
-    RET(alltoallv(X, s_idx, scnt, B.r_idx, rcnt, sizeof(u32), s_val, B.r_val));
+    RET(alltoallv(X, s_idx, B.r_idx, sizeof(u32), C, false, BUF_HOME_IDX, s_val, B.r_val, BUF_HOME_VAL));
     X.pt.stop("home.alltoall");
     // The pairs arrive as one run per sender.  Scattered as they are, every 32-byte sector of the shard
     // would be touched once per sender, far apart in time, and be read-modified-written each time (measured
@@ -680,6 +810,13 @@ extern "C" int bzap_compress_block_distributed(bzap_ctx *ctx, const uint8_t *d_t
         !d_range_cnt || !d_actctl || !d_cnt)
         return bzap_fail(ctx, BZAP_ERR_NOMEM, "distributed block scratch");
     const size_t arena_mark = ctx->arena_off;
+    {
+        const u64 offs[4] = {(u64)((u8 *)home_idx - ctx->arena), (u64)((u8 *)home_val - ctx->arena), (u64)((u8 *)req_in - ctx->arena),
+                             (u64)((u8 *)d_r2 - ctx->arena)};
+        CU(ctx, cudaMemsetAsync(X.d_small + (size_t)G * 1024 - 8, 0, 8 * sizeof(u32), ctx->stream));
+        RET(peers_setup(X, offs));
+        st.peer_windows = X.p2p ? 1u : 0u;
+    }
 
     // ---- 1. select + sort + sparse ranks -------------------------------------------------------------------------
     u64 *keys = nullptr;
@@ -748,20 +885,21 @@ extern "C" int bzap_compress_block_distributed(bzap_ctx *ctx, const uint8_t *d_t
         pt.stop("pull.request+bucket");
         u64 *bk = G > 1 ? K1 : K0;                   // requests grouped by owner (one owner: nothing to regroup)
         u32 *bidx = G > 1 ? V1 : act_idx;
-        u64 scnt[DIST_MAX_WORLD] = {M}, rcnt[DIST_MAX_WORLD] = {M}, total_req = M;
+        u64 total_req = M;
         if (G > 1) {
             u32 *h_all = nullptr;
             RET(gather_words(X, d_h256, 256, &h_all));
             pt.stop("pull.counts");
-            counts_from_hists(geo, h_all, scnt, rcnt);
+            CountMatrix C;
+            matrix_from_hists(geo, h_all, &C);
             total_req = 0;
-            for (int s = 0; s < G; ++s) total_req += rcnt[s];
+            for (int s = 0; s < G; ++s) total_req += C.c[s][me];
             if (total_req > shard) return bzap_fail(ctx, BZAP_ERR_CUDA, "pull: %llu requests for a shard of %u", (unsigned long long)total_req, shard);
-            RET(alltoallv(X, bk, scnt, req_in, rcnt, sizeof(u64)));
+            RET(alltoallv(X, bk, req_in, sizeof(u64), C, false, BUF_REQ_IN));
             pt.stop("pull.alltoall requests");
             if (total_req) LAUNCH(ctx, dist_respond_kernel, grid_1d(total_req, 256 * 4), 256, 0, req_in, (u32)total_req, rank_home, lo, resp_out);
             pt.stop("pull.respond");
-            RET(alltoallv(X, resp_out, rcnt, d_r2, scnt, sizeof(u32)));
+            RET(alltoallv(X, resp_out, d_r2, sizeof(u32), C, true, BUF_R2));
             pt.stop("pull.alltoall responses");
         } else if (M) {
             LAUNCH(ctx, dist_respond_kernel, grid_1d(M, 256 * 4), 256, 0, bk, M, rank_home, lo, d_r2);

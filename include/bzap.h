@@ -76,7 +76,7 @@ typedef struct {
 typedef struct {
     int32_t world, rank;
     uint32_t rounds;                        /* prefix-doubling rounds, the 8-byte key sort included  */
-    uint32_t reserved;
+    uint32_t peer_windows;                  /* 1 = bulk exchanges went through CUDA IPC peer windows, 0 = ncclSend/Recv */
     uint64_t own_rotations;                 /* rotations whose 8-byte key this rank owns             */
     uint64_t exchanged_bytes;               /* bytes this rank sent to peers (all phases)            */
     double ms_total, ms_select_sort, ms_home, ms_rounds, ms_pull, ms_round_sort, ms_tail;

@@ -57,7 +57,9 @@ def make_comm(ctx, rank, world):
     ctx.comm_init(box[0], world, rank)
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, no_p2p=False):
+    if no_p2p:
+        os.environ["BZAP_DIST_NO_P2P"] = "1"      # bulk exchanges through ncclSend/ncclRecv groups instead of peer windows
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                       LOCAL_RANK=str(rank))
     import bwt_mtf_huffman_compressor_b200 as bz
@@ -74,6 +76,7 @@ def _worker(rank, world, port, q):
         ln = ctx.compress_block_distributed(text.data_ptr(), d.size, dst.data_ptr() if rank == 0 else 0, cap)
         s = ctx.dist_stats()
         assert s.world == world and s.rank == rank
+        assert not (no_p2p and s.peer_windows)
         out[name] = dst[:ln].cpu().numpy().tobytes() if rank == 0 else None
     if world > 1:
         dist.barrier()
@@ -83,7 +86,7 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def _run(world):
+def _run(world, no_p2p=False):
     import oracle_lib as O
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -91,7 +94,7 @@ def _run(world):
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, no_p2p)) for r in range(world)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=900) for _ in procs)
@@ -110,6 +113,11 @@ def test_distributed_block_world1():
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_distributed_block_world2():
     _run(2)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_distributed_block_world2_nccl_only():
+    _run(2, no_p2p=True)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 4, reason="needs four GPUs")
