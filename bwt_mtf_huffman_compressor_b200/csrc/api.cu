@@ -631,123 +631,3 @@ extern "C" int bzap_huff_decode(bzap_ctx *ctx, const uint8_t *payload, size_t pa
     if (rc != BZAP_OK) return rc;
     return stage_out(ctx, out, d_out, n);
 }
-
-// ---- device-level building blocks for the distributed single-block path ----------------------------------
-// (one 1 GiB block sorted by prefix doubling over several GPUs: the collectives live in
-//  bwt_mtf_huffman_compressor_b200/distributed.py on torch.distributed/NCCL, the per-GPU work is here)
-#define DEV_ENTER(bytes)                                                                          \
-    RESOLVE(ctx);                                                                                 \
-    RET(arena_reserve(ctx, (bytes)))
-
-extern "C" int bzap_dev_init_keys(bzap_ctx *ctx, const uint8_t *d_text, size_t n, size_t lo, size_t m, uint64_t *d_keys)
-{
-    if (!d_text || !d_keys || n == 0 || n > BZAP_MAX_BLOCK || lo + m > n) return BZAP_ERR_ARG;
-    DEV_ENTER(1u << 20);
-    RET(dev_init_keys(ctx, d_text, (u32)n, (u32)lo, (u32)m, (u64 *)d_keys));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    return BZAP_OK;
-}
-extern "C" int bzap_dev_sort_pairs(bzap_ctx *ctx, uint64_t *d_keys, uint32_t *d_vals, size_t m, uint64_t *d_keys_tmp,
-                                   uint32_t *d_vals_tmp, int *result_in_tmp)
-{
-    if (!d_keys || !d_vals || !d_keys_tmp || !d_vals_tmp || !result_in_tmp || m > BZAP_MAX_BLOCK) return BZAP_ERR_ARG;
-    if (m == 0) { *result_in_tmp = 0; return BZAP_OK; }
-    DEV_ENTER(sort_scratch_bytes((u32)m) + (1u << 20));
-    RET(dev_sort_pairs_generic(ctx, (u64 *)d_keys, d_vals, (u32)m, (u64 *)d_keys_tmp, d_vals_tmp, result_in_tmp));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    return BZAP_OK;
-}
-extern "C" int bzap_dev_rerank(bzap_ctx *ctx, const uint64_t *d_keys_sorted, size_t m, uint32_t pos_base, uint32_t *d_rs,
-                               uint32_t counts[2])
-{
-    if (!d_keys_sorted || !d_rs || !counts || m == 0 || m > BZAP_MAX_BLOCK) return BZAP_ERR_ARG;
-    DEV_ENTER(m / 64 + (1u << 20));
-    return dev_rerank_run(ctx, (const u64 *)d_keys_sorted, (u32)m, pos_base, d_rs, counts);
-}
-extern "C" int bzap_dev_partition_dest(bzap_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_vals, size_t m,
-                                       const uint64_t *split_keys, const uint32_t *split_vals, int n_split, uint8_t *d_dest)
-{
-    if (!d_keys || !d_vals || !d_dest || (n_split && (!split_keys || !split_vals)) || m > BZAP_MAX_BLOCK) return BZAP_ERR_ARG;
-    if (m == 0) return BZAP_OK;
-    DEV_ENTER(1u << 20);
-    return dev_partition_dest(ctx, (const u64 *)d_keys, d_vals, (u32)m, (const u64 *)split_keys, split_vals, n_split, d_dest);
-}
-extern "C" int bzap_dev_stable_perm_by_byte(bzap_ctx *ctx, const uint8_t *d_bytes, size_t m, uint32_t *d_perm, uint32_t cum[257])
-{
-    if (!d_bytes || !d_perm || !cum || m == 0 || m > BZAP_MAX_BLOCK) return BZAP_ERR_ARG;
-    DEV_ENTER(sort_scratch_bytes((u32)m) + (1u << 20));
-    u32 *d_cum = arena_get<u32>(ctx, 260);
-    if (!d_cum) return bzap_fail(ctx, BZAP_ERR_NOMEM, "perm scratch");
-    RET(dev_sort_positions_by_byte(ctx, d_bytes, (u32)m, d_perm, d_cum));
-    u32 *h = (u32 *)(ctx->mailbox + 24576);
-    CU(ctx, cudaMemcpyAsync(h, d_cum, 257 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    memcpy(cum, h, 257 * sizeof(u32));
-    return BZAP_OK;
-}
-extern "C" int bzap_dev_permute_pairs(bzap_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_vals, const uint32_t *d_perm,
-                                      size_t m, uint64_t *d_out_keys, uint32_t *d_out_vals)
-{
-    if (!d_vals || !d_perm || !d_out_vals || (d_keys && !d_out_keys) || m > BZAP_MAX_BLOCK) return BZAP_ERR_ARG;
-    if (m == 0) return BZAP_OK;
-    RESOLVE(ctx);
-    return dev_permute_pairs(ctx, (const u64 *)d_keys, d_vals, d_perm, (u32)m, (u64 *)d_out_keys, d_out_vals);
-}
-extern "C" int bzap_dev_scatter_u32(bzap_ctx *ctx, const uint32_t *d_idx, const uint32_t *d_vals, size_t m, uint32_t idx_offset,
-                                    uint32_t *d_out)
-{
-    if (!d_idx || !d_vals || !d_out || m > BZAP_MAX_BLOCK) return BZAP_ERR_ARG;
-    if (m == 0) return BZAP_OK;
-    RESOLVE(ctx);
-    return dev_scatter_offset(ctx, d_idx, d_vals, (u32)m, idx_offset, d_out);
-}
-extern "C" int bzap_dev_bwt_finish(bzap_ctx *ctx, const uint8_t *d_text, size_t n, uint32_t *d_sa, uint32_t *d_rank, uint32_t *d_rs,
-                                   uint64_t k, uint8_t *d_last, uint64_t *primary)
-{
-    if (!d_text || !d_sa || !d_rank || !d_rs || !d_last || !primary || n == 0 || n > BZAP_MAX_BLOCK) return BZAP_ERR_ARG;
-    DEV_ENTER(22 * n + sort_scratch_bytes((u32)(n / 2 + 1)) + (8u << 20));
-    return dev_bwt_finish(ctx, d_text, (u32)n, d_sa, d_rank, d_rs, k, d_last, primary);
-}
-extern "C" int bzap_dev_bucket_by_index(bzap_ctx *ctx, const uint32_t *d_idx, const uint32_t *d_vals, size_t m, int shift,
-                                        uint32_t *d_idx_out, uint32_t *d_vals_out, uint32_t counts[256])
-{
-    if (!d_idx || !d_vals || !d_idx_out || !d_vals_out || !counts || m > BZAP_MAX_BLOCK || shift < 0 || shift > 24) return BZAP_ERR_ARG;
-    if (m == 0) { memset(counts, 0, 256 * sizeof(uint32_t)); return BZAP_OK; }
-    DEV_ENTER(sort_scratch_bytes((u32)m) / 4 + (1u << 20));
-    return dev_bucket_u32(ctx, d_idx, d_vals, (u32)m, shift, d_idx_out, d_vals_out, counts);
-}
-extern "C" int bzap_dev_gather_last(bzap_ctx *ctx, const uint8_t *d_text, size_t n, const uint32_t *d_sa, size_t m, uint8_t *d_last)
-{
-    if (!d_text || !d_sa || !d_last || n == 0 || n > BZAP_MAX_BLOCK || m > n) return BZAP_ERR_ARG;
-    if (m == 0) return BZAP_OK;
-    RESOLVE(ctx);
-    return dev_gather_slots(ctx, d_text, d_sa, (u32)n, (u32)m, d_last);
-}
-// last column + primary index -> reference-format file (the stages after bwt(), main.cpp:309-324)
-extern "C" int bzap_compress_from_bwt_device(bzap_ctx *ctx, const uint8_t *d_last, size_t n, uint64_t primary, uint8_t *d_out,
-                                             size_t out_cap, size_t *out_len)
-{
-    RESOLVE(ctx);
-    if (!d_last || !d_out || !out_len) return bzap_fail(ctx, BZAP_ERR_ARG, "null pointer");
-    if (n == 0) return bzap_fail(ctx, BZAP_ERR_EMPTY, "empty input");
-    if (n > BZAP_MAX_BLOCK || primary >= n) return bzap_fail(ctx, BZAP_ERR_ARG, "bad block");
-    RET(arena_reserve(ctx, 4 * (n + 1024) + 2 * (n / 128 + 4096) * 1280 + (8u << 20)));
-    const u8 *d_in = d_last;
-    if (((uintptr_t)d_last & 15) != 0) {
-        u8 *d = arena_get<u8>(ctx, n + 64);
-        if (!d) return bzap_fail(ctx, BZAP_ERR_NOMEM, "input staging");
-        CU(ctx, cudaMemcpyAsync(d, d_last, n, cudaMemcpyDeviceToDevice, ctx->stream));
-        d_in = d;
-    }
-    CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-    u8 *d_file = nullptr;
-    size_t len = 0;
-    RET(pipeline_after_bwt(ctx, d_in, n, primary, &d_file, &len));
-    if (len > out_cap) return bzap_fail(ctx, BZAP_ERR_CAPACITY, "need %zu bytes, have %zu", len, out_cap);
-    CU(ctx, cudaMemcpyAsync(d_out, d_file, len, cudaMemcpyDeviceToDevice, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    CU(ctx, cudaGetLastError());
-    finish_stats(ctx);
-    *out_len = len;
-    return BZAP_OK;
-}

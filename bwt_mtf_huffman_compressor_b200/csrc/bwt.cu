@@ -549,34 +549,6 @@ static int bwt_active_rounds(bzap_ctx *ctx, u32 n, u32 m, u64 *k_io, const Activ
     return BZAP_OK;
 }
 
-// per-range survivor counts for bwt_collect_active_kernel when the re-rank kernel did not run here
-__global__ void __launch_bounds__(RR_BLOCK)
-bwt_count_active_kernel(const u32 *__restrict__ rs, u32 n, u32 ntiles, u32 *__restrict__ block_active, u32 *total)
-{
-    __shared__ u32 s_tmp[40];
-    const u32 tid = threadIdx.x;
-    const u32 tpb = (ntiles + gridDim.x - 1) / gridDim.x;
-    const u32 t0 = blockIdx.x * tpb, t1 = min(ntiles, t0 + tpb);
-    u32 cnt = 0;
-    for (u32 tile = t0; tile < t1; ++tile) {
-        const u32 j0 = tile * RR_TILE + tid * RR_ITEMS;
-#pragma unroll
-        for (int i = 0; i < RR_ITEMS; ++i) {
-            u32 j = j0 + i;
-            if (j < n) {
-                u32 r0 = rs[j], r1 = j + 1 < n ? rs[j + 1] : j + 1;
-                cnt += !(r0 == j && r1 == j + 1);
-            }
-        }
-    }
-    u32 tot;
-    block_exclusive_sum(cnt, s_tmp, &tot);
-    if (tid == 0) {
-        block_active[blockIdx.x] = tot;
-        if (tot) atomicAdd(total, tot);
-    }
-}
-
 int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
 {
     if (n64 == 0) return bzap_fail(ctx, BZAP_ERR_EMPTY, "empty input");
@@ -707,37 +679,9 @@ int dev_bwt(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_last, u64 *primary)
     return BZAP_OK;
 }
 
-// ---- device-level building blocks for the distributed single-block path (include/bzap.h) ----------------
-int dev_init_keys(bzap_ctx *ctx, const u8 *d_text, u32 n, u32 lo, u32 m, u64 *d_keys)
-{
-    LAUNCH(ctx, bwt_init_keys_kernel, grid_for((m + IK_TILE - 1) / IK_TILE, 1, 148 * 8), IK_BLOCK, 0, d_text, n, lo, m, d_keys);
-    CU(ctx, cudaGetLastError());
-    return BZAP_OK;
-}
-
-// sparse ranks of an already sorted key run whose first element sits at global slot pos_base;
-// counts[0] = heads, counts[1] = singleton groups (both local: the caller patches the seams)
-int dev_rerank_run(bzap_ctx *ctx, const u64 *d_keys, u32 m, u32 pos_base, u32 *d_rs, u32 counts[2])
-{
-    const u32 rr_tiles = (m + RR_TILE - 1) / RR_TILE;
-    const size_t words = 4 * 256 + 8 + 2 * ((size_t)rr_tiles + 8);
-    u32 *d_ctl = arena_get<u32>(ctx, words);
-    if (!d_ctl) return bzap_fail(ctx, BZAP_ERR_NOMEM, "rerank scratch");
-    CU(ctx, cudaMemsetAsync(d_ctl, 0, words * sizeof(u32), ctx->stream));
-    u32 *d_hist4 = d_ctl, *d_counters = d_ctl + 4 * 256;
-    u64 *d_status = (u64 *)(d_ctl + 4 * 256 + 8);
-    LAUNCH(ctx, bwt_rerank_kernel, grid_for(rr_tiles, 1, 148 * 6), RR_BLOCK, 0, d_keys, (const u32 *)nullptr, m, rr_tiles,
-           pos_base, (u32 *)nullptr, d_rs, d_hist4, d_counters, d_status, (u32 *)nullptr);
-    u32 *h = (u32 *)(ctx->mailbox + 1024);
-    CU(ctx, cudaMemcpyAsync(h, d_counters, 2 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    CU(ctx, cudaGetLastError());
-    counts[0] = h[0];
-    counts[1] = h[1];
-    return BZAP_OK;
-}
-
-// the same without a host round trip (dist_block.cu): d_ctl = rerank_ctl_words(m) zeroed words whose
+// ---- building blocks shared with the distributed single-block path (dist_block.cu) --------------------------
+// sparse ranks of an already sorted key run whose first element sits at global slot pos_base,
+// without a host round trip: d_ctl = rerank_ctl_words(m) zeroed words whose
 // words [1024] / [1025] end up holding {groups, singleton groups}; d_bact (148 * 6 + 8 words) receives the
 // per-range survivor counts that dev_collect_active consumes
 size_t rerank_ctl_words(u32 m)
@@ -800,69 +744,5 @@ int dev_gather_slots(bzap_ctx *ctx, const u8 *d_text, const u32 *d_sa, u32 n, u3
     else LAUNCH(ctx, bwt_gather_slots_kernel, grid_for(m, 256), 256, 0, d_text, d_sa, n, m, d_last);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     CU(ctx, cudaGetLastError());
-    return BZAP_OK;
-}
-
-// Finishes a BWT whose first rounds were done elsewhere (the distributed path hands over once few
-// rotations are unsettled): d_sa = suffix array so far, d_rs = sparse ranks in suffix-array order,
-// d_rank = the same ranks in text order, all for prefix length k.  Runs active rounds to the end,
-// then writes the last column.  d_rs is clobbered.
-int dev_bwt_finish(bzap_ctx *ctx, const u8 *d_text, u32 n, u32 *d_sa, u32 *d_rank, u32 *d_rs, u64 k, u8 *d_last, u64 *primary)
-{
-    const u32 rr_tiles = (n + RR_TILE - 1) / RR_TILE;
-    const u32 rr_grid = grid_for(rr_tiles, 1, 148 * 6);
-    u32 *d_bact = arena_get<u32>(ctx, 148 * 6 + 8);
-    if (!d_bact) return bzap_fail(ctx, BZAP_ERR_NOMEM, "bwt scratch");
-    u32 *d_total = d_bact + 148 * 6 + 2;
-    CU(ctx, cudaMemsetAsync(d_total, 0, sizeof(u32), ctx->stream));
-    LAUNCH(ctx, bwt_count_active_kernel, rr_grid, RR_BLOCK, 0, d_rs, n, rr_tiles, d_bact, d_total);
-    u32 *h_cnt = (u32 *)(ctx->mailbox + 1024);
-    CU(ctx, cudaMemcpyAsync(h_cnt, d_total, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    const u32 m = h_cnt[0];
-    u32 rounds = 0, passes_total = 0;
-    if (m && k < n) {
-        const u32 mt = (m + AC_TILE - 1) / AC_TILE;
-        ActiveWork w;
-        w.ab.keys[0] = arena_get<u64>(ctx, m);
-        w.ab.keys[1] = arena_get<u64>(ctx, m);
-        w.ab.vals[0] = arena_get<u32>(ctx, m);
-        w.ab.vals[1] = arena_get<u32>(ctx, m);
-        w.act_r1 = arena_get<u32>(ctx, m);
-        w.newr = arena_get<u32>(ctx, m);
-        w.pos = arena_get<u32>(ctx, m);
-        w.next_idx = arena_get<u32>(ctx, m);
-        w.next_r1 = arena_get<u32>(ctx, m);
-        w.d_hist8 = arena_get<u32>(ctx, 8 * 256);
-        const size_t status_u64 = 2 * ((size_t)mt + 2) + 8;
-        w.d_rrctl = arena_get<u32>(ctx, 4 * 256 + 8 + 2 * status_u64);
-        w.cstatus = arena_get<u64>(ctx, (size_t)mt + 4);
-        if (!w.ab.keys[0] || !w.ab.keys[1] || !w.ab.vals[0] || !w.ab.vals[1] || !w.act_r1 || !w.newr || !w.pos || !w.next_idx ||
-            !w.next_r1 || !w.d_hist8 || !w.d_rrctl || !w.cstatus)
-            return bzap_fail(ctx, BZAP_ERR_NOMEM, "bwt scratch");
-        w.rrctl_bytes = (4 * 256 + 8 + 2 * status_u64) * sizeof(u32);
-        w.d_counters = w.d_rrctl + 4 * 256;
-        w.d_ticket = w.d_counters + 4;
-        w.d_status = (u64 *)(w.d_rrctl + 4 * 256 + 8);
-        w.sa_buf = d_sa;
-        w.d_rank = d_rank;
-        w.arena_mark = ctx->arena_off;
-        u32 rank_bits = 1;
-        while (rank_bits < 32 && (1ull << rank_bits) < n) ++rank_bits;
-        const u32 nd = (rank_bits + 7) / 8;
-        w.rank_mask = ((1u << nd) - 1u) | (((1u << nd) - 1u) << 4);
-        w.zero_base = (u8 *)w.d_hist8;
-        w.zero_bytes = (size_t)((u8 *)(w.cstatus + mt + 4) - (u8 *)w.d_hist8);
-        LAUNCH(ctx, bwt_collect_active_kernel, rr_grid, RR_BLOCK, 0, d_rs, d_sa, n, rr_tiles, 0u, d_bact, w.ab.vals[0], w.act_r1);
-        RET(bwt_active_rounds(ctx, n, m, &k, w, &rounds, &passes_total));
-    }
-    LAUNCH(ctx, bwt_gather_kernel, grid_for((n + 3) / 4, 256), 256, 0, d_text, d_sa, n, n, d_last);
-    u32 *h_primary = (u32 *)(ctx->mailbox + 1040);
-    CU(ctx, cudaMemcpyAsync(h_primary, d_rank, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    CU(ctx, cudaGetLastError());
-    *primary = *h_primary;
-    ctx->stats.bwt_rounds = rounds;
-    ctx->stats.bwt_sort_passes = passes_total;
     return BZAP_OK;
 }

@@ -165,24 +165,13 @@ int dev_sort_pairs64(bzap_ctx *ctx, SortBuffers *b, u32 n, u32 pass_mask, const 
 // (main.cpp:67); d_cum receives the 257 exclusive byte counts
 int dev_sort_positions_by_byte(bzap_ctx *ctx, const u8 *d_bytes, u32 n, u32 *d_T, u32 *d_cum);
 size_t sort_scratch_bytes(u32 n);
-// building blocks of the distributed single-block path
-int dev_init_keys(bzap_ctx *ctx, const u8 *d_text, u32 n, u32 lo, u32 m, u64 *d_keys);
-int dev_bwt_finish(bzap_ctx *ctx, const u8 *d_text, u32 n, u32 *d_sa, u32 *d_rank, u32 *d_rs, u64 k, u8 *d_last, u64 *primary);
-int dev_rerank_run(bzap_ctx *ctx, const u64 *d_keys, u32 m, u32 pos_base, u32 *d_rs, u32 counts[2]);
+// building blocks shared with the distributed single-block path (dist_block.cu)
 size_t rerank_ctl_words(u32 m);
 int dev_rerank_sorted(bzap_ctx *ctx, const u64 *d_keys, u32 m, u32 pos_base, u32 *d_rs, u32 *d_ctl, u32 *d_bact);
 int dev_collect_active(bzap_ctx *ctx, const u32 *d_rs, const u32 *d_sa, u32 m, u32 pos_base, const u32 *d_bact, u32 *act_idx,
                        u32 *act_r1);
 size_t active_ctl_bytes(u32 m, ActiveWork *w, u8 *base);   // lays the per-round control block of the active rounds out at base
-int dev_sort_pairs_generic(bzap_ctx *ctx, u64 *d_keys, u32 *d_vals, u32 m, u64 *d_keys_tmp, u32 *d_vals_tmp,
-                           int *result_in_tmp);
-int dev_permute_pairs(bzap_ctx *ctx, const u64 *d_keys, const u32 *d_vals, const u32 *d_perm, u32 m, u64 *d_out_k, u32 *d_out_v);
-int dev_scatter_offset(bzap_ctx *ctx, const u32 *d_idx, const u32 *d_vals, u32 m, u32 off, u32 *d_out);
 int dev_gather_slots(bzap_ctx *ctx, const u8 *d_text, const u32 *d_sa, u32 n, u32 m, u8 *d_last);
-int dev_bucket_u32(bzap_ctx *ctx, const u32 *d_keys, const u32 *d_vals, u32 m, int shift, u32 *d_keys_out, u32 *d_vals_out,
-                   u32 h_counts[256]);
-int dev_partition_dest(bzap_ctx *ctx, const u64 *d_keys, const u32 *d_vals, u32 m, const u64 *h_sk, const u32 *h_sv, int ns,
-                       u8 *d_dest);
 size_t bucket_ctl_words(u32 m);
 int dev_bucket_pass_u64(bzap_ctx *ctx, const u64 *d_keys, const u32 *d_vals, u32 m, int shift, u64 *d_keys_out, u32 *d_vals_out,
                         const u32 *d_hist256, u32 *d_ctl);

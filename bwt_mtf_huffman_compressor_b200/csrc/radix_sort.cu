@@ -573,116 +573,12 @@ int dev_scatter_perm(bzap_ctx *ctx, const u32 *d_perm, const u32 *d_vals, u32 n,
     return BZAP_OK;
 }
 
-// ---- generic 64-bit pair sort with its own digit histograms (distributed path, device pointers) -----------
-__global__ void __launch_bounds__(256) radix_hist_u64_kernel(const u64 *__restrict__ keys, u32 n, u32 *hist8)
-{
-    __shared__ u32 s_h[8 * 256];
-    for (u32 i = threadIdx.x; i < 8 * 256; i += 256) s_h[i] = 0;
-    __syncthreads();
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        u64 k = keys[i];
-#pragma unroll
-        for (int p = 0; p < 8; ++p) atomicAdd(&s_h[p * 256 + ((u32)(k >> (8 * p)) & 0xffu)], 1u);
-    }
-    __syncthreads();
-    for (u32 i = threadIdx.x; i < 8 * 256; i += 256) {
-        u32 c = s_h[i];
-        if (c) atomicAdd(&hist8[i], c);
-    }
-}
-
-int dev_sort_pairs_generic(bzap_ctx *ctx, u64 *d_keys, u32 *d_vals, u32 m, u64 *d_keys_tmp, u32 *d_vals_tmp,
-                           int *result_in_tmp)
-{
-    u32 *d_hist8 = arena_get<u32>(ctx, 8 * 256);
-    if (!d_hist8) return bzap_fail(ctx, BZAP_ERR_NOMEM, "sort scratch");
-    CU(ctx, cudaMemsetAsync(d_hist8, 0, 8 * 256 * sizeof(u32), ctx->stream));
-    LAUNCH(ctx, radix_hist_u64_kernel, min((m + 255) / 256, 148u * 8u), 256, 0, d_keys, m, d_hist8);
-    SortBuffers sb;
-    sb.keys[0] = d_keys; sb.keys[1] = d_keys_tmp;
-    sb.vals[0] = d_vals; sb.vals[1] = d_vals_tmp;
-    u64 *ok = nullptr;
-    u32 *ov = nullptr;
-    int passes = 0;
-    RET(dev_sort_pairs64(ctx, &sb, m, 0xffu, d_hist8, 8, false, &ok, &ov, &passes));
-    *result_in_tmp = ok == d_keys_tmp;
-    return BZAP_OK;
-}
-
-// dest[i] = number of splitters (K, I) with (K, I) <= (key[i], val[i]) lexicographically
-__global__ void __launch_bounds__(256)
-partition_dest_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ vals, u32 m, const u64 *__restrict__ sk,
-                      const u32 *__restrict__ sv, int ns, u8 *__restrict__ dest)
-{
-    __shared__ u64 s_k[256];
-    __shared__ u32 s_v[256];
-    if ((int)threadIdx.x < ns) { s_k[threadIdx.x] = sk[threadIdx.x]; s_v[threadIdx.x] = sv[threadIdx.x]; }
-    __syncthreads();
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
-        u64 k = keys[i];
-        u32 v = vals[i];
-        int lo = 0, hi = ns;                       // first splitter greater than (k, v)
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            bool le = s_k[mid] < k || (s_k[mid] == k && s_v[mid] <= v);
-            if (le) lo = mid + 1; else hi = mid;
-        }
-        dest[i] = (u8)lo;
-    }
-}
-
-int dev_partition_dest(bzap_ctx *ctx, const u64 *d_keys, const u32 *d_vals, u32 m, const u64 *h_sk, const u32 *h_sv, int ns,
-                       u8 *d_dest)
-{
-    if (ns < 0 || ns > 255) return bzap_fail(ctx, BZAP_ERR_ARG, "splitters");
-    u64 *d_sk = arena_get<u64>(ctx, 256);
-    u32 *d_sv = arena_get<u32>(ctx, 256);
-    if (!d_sk || !d_sv) return bzap_fail(ctx, BZAP_ERR_NOMEM, "partition scratch");
-    u64 *m_sk = (u64 *)(ctx->mailbox + 20480);
-    u32 *m_sv = (u32 *)(ctx->mailbox + 20480 + 2048);
-    for (int i = 0; i < ns; ++i) { m_sk[i] = h_sk[i]; m_sv[i] = h_sv[i]; }
-    if (ns) {
-        CU(ctx, cudaMemcpyAsync(d_sk, m_sk, ns * sizeof(u64), cudaMemcpyHostToDevice, ctx->stream));
-        CU(ctx, cudaMemcpyAsync(d_sv, m_sv, ns * sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
-    }
-    LAUNCH(ctx, partition_dest_kernel, min((m + 255) / 256, 148u * 16u), 256, 0, d_keys, d_vals, m, d_sk, d_sv, ns, d_dest);
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    CU(ctx, cudaGetLastError());
-    return BZAP_OK;
-}
-
-// out_k[j] = keys[perm[j]], out_v[j] = vals[perm[j]]  (regrouping by destination before an all-to-all)
-__global__ void __launch_bounds__(256)
-permute_pairs_kernel(const u64 *__restrict__ keys, const u32 *__restrict__ vals, const u32 *__restrict__ perm, u32 m,
-                     u64 *__restrict__ out_k, u32 *__restrict__ out_v)
-{
-    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
-        u32 p = perm[j];
-        if (keys) out_k[j] = keys[p];
-        out_v[j] = vals[p];
-    }
-}
-int dev_permute_pairs(bzap_ctx *ctx, const u64 *d_keys, const u32 *d_vals, const u32 *d_perm, u32 m, u64 *d_out_k, u32 *d_out_v)
-{
-    LAUNCH(ctx, permute_pairs_kernel, min((m + 255) / 256, 148u * 16u), 256, 0, d_keys, d_vals, d_perm, m, d_out_k, d_out_v);
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    CU(ctx, cudaGetLastError());
-    return BZAP_OK;
-}
 // out[idx[j] - idx_offset] = vals[j]
 __global__ void __launch_bounds__(256)
 scatter_offset_kernel(const u32 *__restrict__ idx, const u32 *__restrict__ vals, u32 m, u32 off, u32 *__restrict__ out)
 {
     for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) out[idx[j] - off] = vals[j];
 }
-int dev_scatter_offset(bzap_ctx *ctx, const u32 *d_idx, const u32 *d_vals, u32 m, u32 off, u32 *d_out)
-{
-    LAUNCH(ctx, scatter_offset_kernel, min((m + 255) / 256, 148u * 16u), 256, 0, d_idx, d_vals, m, off, d_out);
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    CU(ctx, cudaGetLastError());
-    return BZAP_OK;
-}
-
 // ---- bucket (index, value) pairs by the top 8 bits of the index (distributed path: ranks go home) --------
 __global__ void __launch_bounds__(256) radix_hist_u32_digit_kernel(const u32 *__restrict__ keys, u32 m, int shift, u32 *hist)
 {
@@ -694,34 +590,6 @@ __global__ void __launch_bounds__(256) radix_hist_u32_digit_kernel(const u32 *__
     __syncthreads();
     u32 c = s_h[threadIdx.x];
     if (c) atomicAdd(&hist[threadIdx.x], c);
-}
-
-int dev_bucket_u32(bzap_ctx *ctx, const u32 *d_keys, const u32 *d_vals, u32 m, int shift, u32 *d_keys_out, u32 *d_vals_out,
-                   u32 h_counts[256])
-{
-    constexpr int ITEMS = RS_ITEMS_32;
-    const u32 tiles = (m + RS_BLOCK * ITEMS - 1) / (RS_BLOCK * ITEMS);
-    const size_t status_words = (size_t)tiles * 256;
-    u32 *d_ctl = arena_get<u32>(ctx, 256 + 264 + 8 + status_words);
-    if (!d_ctl) return bzap_fail(ctx, BZAP_ERR_NOMEM, "bucket scratch");
-    u32 *d_hist = d_ctl, *d_cum = d_ctl + 256, *d_ticket = d_ctl + 520, *d_status = d_ctl + 528;
-    CU(ctx, cudaMemsetAsync(d_ctl, 0, (528 + status_words) * sizeof(u32), ctx->stream));
-    LAUNCH(ctx, radix_hist_u32_digit_kernel, min((m + 255) / 256, 148u * 8u), 256, 0, d_keys, m, shift, d_hist);
-    LAUNCH(ctx, radix_cum_u8_kernel, 1, 256, 0, d_hist, d_cum, d_ticket + 1);
-    auto k = onesweep_pass_kernel<u32, ITEMS, false, true>;
-    const size_t smem = sizeof(RsSmem<u32, ITEMS>);
-    if (!(ctx->attr_mask & ATTR_SORT32)) {
-        RET(set_smem_attr(ctx, k, smem));
-        ctx->attr_mask |= ATTR_SORT32;
-    }
-    LAUNCH(ctx, k, tiles, RS_BLOCK, smem, d_keys, d_keys_out, d_vals, d_vals_out, m, shift, d_cum, d_status, d_ticket,
-           (const void *)nullptr, 0u, (const u32 *)(d_ticket + 1));
-    u32 *h = (u32 *)(ctx->mailbox + 28672);
-    CU(ctx, cudaMemcpyAsync(h, d_hist, 256 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(ctx, cudaStreamSynchronize(ctx->stream));
-    CU(ctx, cudaGetLastError());
-    memcpy(h_counts, h, 256 * sizeof(u32));
-    return BZAP_OK;
 }
 
 // ---- single bucketing passes without a host round trip (dist_block.cu) ------------------------------------

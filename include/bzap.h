@@ -146,45 +146,6 @@ int bzap_huff_encode(bzap_ctx *ctx, const uint8_t *in, size_t n, const bzap_tree
 int bzap_huff_decode(bzap_ctx *ctx, const uint8_t *payload, size_t payload_len, const bzap_tree *tree,
                      size_t n, uint8_t *out);
 
-/* ---- device-level building blocks (device pointers) for ONE block sorted over several GPUs -------
- * The distributed prefix-doubling sample sort runs one process per GPU; the exchange
- * steps are NCCL collectives issued by the host program (bwt_mtf_huffman_compressor_b200/
- * distributed.py), the per-GPU steps are these calls.  Together they replace bwt() main.cpp:77-91
- * for a block that is spread over the GPUs of one box.                                             */
-/* keys[i] = first 8 bytes (cyclic, big endian) of rotation lo+i, i < m, of the n-byte text         */
-int bzap_dev_init_keys(bzap_ctx *ctx, const uint8_t *d_text, size_t n, size_t lo, size_t m, uint64_t *d_keys);
-/* stable LSD onesweep sort of (key, payload) pairs; *result_in_tmp tells which buffer pair holds it */
-int bzap_dev_sort_pairs(bzap_ctx *ctx, uint64_t *d_keys, uint32_t *d_vals, size_t m, uint64_t *d_keys_tmp,
-                        uint32_t *d_vals_tmp, int *result_in_tmp);
-/* sparse ranks of a sorted run whose first element is global slot pos_base: rs[j] = pos_base + index
- * of the first element with the same key; counts = {groups, singleton groups} inside the run        */
-int bzap_dev_rerank(bzap_ctx *ctx, const uint64_t *d_keys_sorted, size_t m, uint32_t pos_base, uint32_t *d_rs,
-                    uint32_t counts[2]);
-/* dest[i] = number of splitters (K, I) <= (key[i], payload[i]); splitters are host arrays, sorted    */
-int bzap_dev_partition_dest(bzap_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_vals, size_t m,
-                            const uint64_t *split_keys, const uint32_t *split_vals, int n_split, uint8_t *d_dest);
-/* stable counting sort of positions by byte: perm = positions grouped by byte value, cum[257] (host) */
-int bzap_dev_stable_perm_by_byte(bzap_ctx *ctx, const uint8_t *d_bytes, size_t m, uint32_t *d_perm, uint32_t cum[257]);
-/* out_keys[j] = keys[perm[j]] (keys may be NULL), out_vals[j] = vals[perm[j]]                          */
-int bzap_dev_permute_pairs(bzap_ctx *ctx, const uint64_t *d_keys, const uint32_t *d_vals, const uint32_t *d_perm, size_t m,
-                           uint64_t *d_out_keys, uint32_t *d_out_vals);
-/* out[idx[j] - idx_offset] = vals[j]  (ranks written back into the owner's shard)                      */
-int bzap_dev_scatter_u32(bzap_ctx *ctx, const uint32_t *d_idx, const uint32_t *d_vals, size_t m, uint32_t idx_offset,
-                         uint32_t *d_out);
-/* finishes a block whose first doubling rounds ran elsewhere: suffix array so far, ranks in text order
- * and in suffix-array order (clobbered), all for prefix length k -> last column + primary index      */
-int bzap_dev_bwt_finish(bzap_ctx *ctx, const uint8_t *d_text, size_t n, uint32_t *d_sa, uint32_t *d_rank, uint32_t *d_rs,
-                        uint64_t k, uint8_t *d_last, uint64_t *primary);
-/* stable regroup of (index, value) pairs by digit (index >> shift) & 255; counts[256] on the host       */
-int bzap_dev_bucket_by_index(bzap_ctx *ctx, const uint32_t *d_idx, const uint32_t *d_vals, size_t m, int shift,
-                             uint32_t *d_idx_out, uint32_t *d_vals_out, uint32_t counts[256]);
-/* last[j] = text[(sa[j] + n - 1) mod n], j < m  (main.cpp:87 for the slots this GPU holds)             */
-int bzap_dev_gather_last(bzap_ctx *ctx, const uint8_t *d_text, size_t n, const uint32_t *d_sa, size_t m, uint8_t *d_last);
-/* the stages after bwt() (main.cpp:309-324): last column + primary index -> reference-format file    */
-int bzap_compress_from_bwt_device(bzap_ctx *ctx, const uint8_t *d_last, size_t n, uint64_t primary, uint8_t *d_out,
-                                  size_t out_cap, size_t *out_len);
-
-
 /* ---- ONE block sorted over several GPUs (BASELINE config 5 ii) -----------------------
  * Replaces bwt() + move_to_front() + huffman() + write_bytes() (main.cpp:304-324) for a block that
  * is spread over the GPUs of one box: one process (or thread) per GPU, each with its own context;
