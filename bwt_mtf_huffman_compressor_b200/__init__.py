@@ -96,7 +96,11 @@ def lib():
         "bzap_compress_device": (C.c_int, [vp, vp, sz, vp, sz, szp]),
         "bzap_decompress_device": (C.c_int, [vp, vp, sz, vp, sz, szp]),
         "bzap_compress_batch": (C.c_int, [C.POINTER(vp), szp, C.POINTER(vp), szp, C.c_int, C.c_int]),
-        "bzap_decompress_batch": (C.c_int, [C.POINTER(vp), szp, C.POINTER(vp), szp, C.c_int, C.c_int]),
+        "bzap_decompress_batch": (C.c_int, [C.POINTER(vp), szp, C.POINTER(vp), szp, szp, C.c_int, C.c_int]),
+        "bzap_compress_batch_gpus": (C.c_int, [C.POINTER(vp), szp, C.POINTER(vp), szp, C.c_int, C.c_int, C.c_int]),
+        "bzap_decompress_batch_gpus": (C.c_int, [C.POINTER(vp), szp, C.POINTER(vp), szp, szp, C.c_int, C.c_int, C.c_int]),
+        "bzap_compress_files": (C.c_int, [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int]),
+        "bzap_decompress_files": (C.c_int, [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int]),
         "bzap_bwt": (C.c_int, [vp, vp, sz, vp, C.POINTER(C.c_uint64)]),
         "bzap_ibwt": (C.c_int, [vp, vp, sz, C.c_uint64, vp]),
         "bzap_mtf": (C.c_int, [vp, vp, sz, vp]),
@@ -247,12 +251,14 @@ def decompress_bytes(blob, ctx=None):
     c = _ctx(ctx)
     a = _u8(blob)
     n = decompressed_size(a)
+    if n > (1 << 30):
+        raise BzapError(ERR_TOO_LARGE, "header asks for %d bytes" % n)      # before allocating anything
     out = np.empty(max(n, 1), dtype=np.uint8)
     got = c.decompress_ptr(a.ctypes.data, a.size, out.ctypes.data, n)
     return out[:got].copy()
 
 
-def _batch(fn, blobs, sizes_out, n_streams):
+def _batch(compress, blobs, sizes_out, n_streams, n_gpus):
     L = lib()
     k = len(blobs)
     arrs = [_u8(b) for b in blobs]
@@ -261,19 +267,62 @@ def _batch(fn, blobs, sizes_out, n_streams):
     ns = (C.c_size_t * k)(*[a.size for a in arrs])
     outs_p = (C.c_void_p * k)(*[o.ctypes.data for o in outs])
     lens = (C.c_size_t * k)()
-    rc = getattr(L, fn)(ins_p, ns, outs_p, lens, k, n_streams)
+    if compress:
+        rc = L.bzap_compress_batch_gpus(ins_p, ns, outs_p, lens, k, n_gpus, n_streams)
+    else:
+        caps = (C.c_size_t * k)(*[int(s) for s in sizes_out])
+        rc = L.bzap_decompress_batch_gpus(ins_p, ns, outs_p, caps, lens, k, n_gpus, n_streams)
     if rc != BZAP_OK:
-        raise BzapError(rc, fn)
+        raise BzapError(rc, "bzap_%s_batch" % ("compress" if compress else "decompress"))
     return [o[:lens[i]].copy() for i, o in enumerate(outs)]
 
 
-def compress_batch(datas, n_streams=0):
-    """Independent inputs, one BWT block each (the reference's 14-file loop, main.cpp:424-437)."""
-    return _batch("bzap_compress_batch", datas, [compress_bound(len(_u8(d))) for d in datas], n_streams)
+def compress_batch(datas, n_streams=0, n_gpus=0):
+    """Independent inputs, one BWT block each (the reference's 14-file loop, main.cpp:424-437), over
+    n_streams workers on each of n_gpus devices (0 = the current device)."""
+    return _batch(True, datas, [compress_bound(len(_u8(d))) for d in datas], n_streams, n_gpus)
 
 
-def decompress_batch(blobs, n_streams=0):
-    return _batch("bzap_decompress_batch", blobs, [decompressed_size(b) for b in blobs], n_streams)
+def decompress_batch(blobs, n_streams=0, n_gpus=0):
+    sizes = [decompressed_size(b) for b in blobs]
+    if any(s > (1 << 30) for s in sizes):
+        raise BzapError(ERR_TOO_LARGE, "header asks for more than BZAP_MAX_BLOCK")     # before allocating
+    return _batch(False, blobs, sizes, n_streams, n_gpus)
+
+
+def batch_ptrs(compress, in_ptrs, in_lens, out_ptrs, out_caps, n_streams=0, n_gpus=0):
+    """Raw-pointer form for pinned host buffers (bench.py): returns the output lengths."""
+    k = len(in_ptrs)
+    ins_p = (C.c_void_p * k)(*in_ptrs)
+    ns = (C.c_size_t * k)(*in_lens)
+    outs_p = (C.c_void_p * k)(*out_ptrs)
+    lens = (C.c_size_t * k)()
+    if compress:
+        rc = lib().bzap_compress_batch_gpus(ins_p, ns, outs_p, lens, k, n_gpus, n_streams)
+    else:
+        caps = (C.c_size_t * k)(*out_caps)
+        rc = lib().bzap_decompress_batch_gpus(ins_p, ns, outs_p, caps, lens, k, n_gpus, n_streams)
+    if rc != BZAP_OK:
+        raise BzapError(rc, "batch")
+    return [lens[i] for i in range(k)]
+
+
+def compress_files(in_paths, out_paths, n_gpus=0, n_streams=0):
+    k = len(in_paths)
+    a = (C.c_char_p * k)(*[os.fsencode(p) for p in in_paths])
+    b = (C.c_char_p * k)(*[os.fsencode(p) for p in out_paths])
+    rc = lib().bzap_compress_files(a, b, k, n_gpus, n_streams)
+    if rc != BZAP_OK:
+        raise BzapError(rc, "bzap_compress_files")
+
+
+def decompress_files(in_paths, out_paths, n_gpus=0, n_streams=0):
+    k = len(in_paths)
+    a = (C.c_char_p * k)(*[os.fsencode(p) for p in in_paths])
+    b = (C.c_char_p * k)(*[os.fsencode(p) for p in out_paths])
+    rc = lib().bzap_decompress_files(a, b, k, n_gpus, n_streams)
+    if rc != BZAP_OK:
+        raise BzapError(rc, "bzap_decompress_files")
 
 
 # ---- stage level: the reference's free functions -----------------------------------------------------

@@ -7,7 +7,10 @@
 // All compute is CUDA; there is no CPU path.  Host work is limited to the <=511-node Huffman
 // model (huffman_host.cpp) and the 24-byte header.
 #include "bzap_internal.h"
+#include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -419,70 +422,165 @@ extern "C" int bzap_decompress_file(bzap_ctx *ctx, const char *in_path, const ch
     return write_file(ctx, out_path, out.data(), len);
 }
 
-// ---- batch: independent files over several streams -----------------------------------------------------
+// ---- batch: independent files, one BWT block each, over the streams of one or several GPUs -------------------
+// Replaces the reference's 14-file loop (main.cpp:424-437).  A persistent pool of worker threads, one per
+// (device, stream slot), each with its own context (stream + scratch arena); a batch call hands the files
+// out largest first (greedy: a free worker takes the largest remaining file), so that on every device the
+// host-to-device copy of one file and the read-back of another overlap the kernels of a third -- the
+// pinned-buffer I/O pipeline that replaces read_bytes / write_bytes (io_utilities.h:7-55) for batches.
 namespace {
-struct Pool {
-    std::mutex mu;
-    std::vector<bzap_ctx *> ctxs;
-    int device = -1;
+struct BatchJob {
+    std::function<int(bzap_ctx *, int)> fn;
+    std::vector<int> order;                     // file indices, largest first
+    std::atomic<int> next{0};
+    std::atomic<int> first_err{BZAP_OK};
+    int dev_lo = 0, dev_hi = 1, n_streams = 1;  // devices dev_lo .. dev_hi-1, stream slots 0 .. n_streams-1 take part
+    int pending = 0;                            // workers that still have to report (guarded by Engine::mu)
 };
-Pool g_pool;
+struct Worker {
+    std::thread th;
+    bzap_ctx *ctx = nullptr;
+    int device = 0, slot = 0;
+};
+struct Engine {
+    std::mutex api_mu;                          // one batch at a time
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::vector<Worker *> workers;
+    BatchJob *job = nullptr;
+    unsigned long long generation = 0;
+};
+Engine *g_engine = nullptr;                     // never destroyed: worker threads outlive main()'s statics
+std::once_flag g_engine_once;
+
+void worker_main(Engine *E, Worker *w)
+{
+    cudaSetDevice(w->device);
+    unsigned long long seen = 0;
+    while (true) {
+        BatchJob *job = nullptr;
+        {
+            std::unique_lock<std::mutex> lk(E->mu);
+            E->cv_work.wait(lk, [&] { return E->generation != seen; });
+            seen = E->generation;
+            job = E->job;
+        }
+        if (!job || w->device < job->dev_lo || w->device >= job->dev_hi || w->slot >= job->n_streams) continue;   // sits this one out
+        const int count = (int)job->order.size();
+        for (int i = job->next.fetch_add(1); i < count; i = job->next.fetch_add(1)) {
+            w->ctx->err[0] = 0;
+            int rc = job->fn(w->ctx, job->order[i]);
+            int ok = BZAP_OK;
+            if (rc != BZAP_OK) job->first_err.compare_exchange_strong(ok, rc);
+        }
+        std::lock_guard<std::mutex> lk(E->mu);
+        if (--job->pending == 0) E->cv_done.notify_all();
+    }
 }
 
-template <typename Fn> static int run_batch(int count, int n_streams, Fn fn)
+// runs fn(ctx, i) for i < count on n_streams workers of each of the devices 0 .. n_gpus-1 (n_gpus = 0: the
+// current device only); sizes[i] orders the hand-out
+int run_batch(int count, const size_t *sizes, int n_gpus, int n_streams, std::function<int(bzap_ctx *, int)> fn)
 {
     if (count <= 0) return BZAP_OK;
+    int have = 0, cur = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess || have == 0) return BZAP_ERR_CUDA;      // fail loudly: no CPU path
+    if (cudaGetDevice(&cur) != cudaSuccess) return BZAP_ERR_CUDA;
     if (n_streams <= 0) n_streams = 4;
-    if (n_streams > count) n_streams = count;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return BZAP_ERR_CUDA;
-    std::lock_guard<std::mutex> g(g_pool.mu);
-    if (g_pool.device != dev) {
-        for (bzap_ctx *c : g_pool.ctxs) bzap_ctx_destroy(c);
-        g_pool.ctxs.clear();
-        g_pool.device = dev;
+    if (n_streams > 32) n_streams = 32;
+    int dev_lo = 0, dev_hi = n_gpus;
+    if (n_gpus <= 0) { dev_lo = cur; dev_hi = cur + 1; }
+    if (dev_hi > have) return BZAP_ERR_ARG;
+    std::call_once(g_engine_once, [] { g_engine = new Engine(); });
+    Engine *E = g_engine;
+    std::lock_guard<std::mutex> api(E->api_mu);
+    // grow the pool: worker (device d, slot s) exists for every pair a batch has asked for so far
+    for (int d = dev_lo; d < dev_hi; ++d)
+        for (int sl = 0; sl < n_streams; ++sl) {
+            bool found = false;
+            for (Worker *w : E->workers) found = found || (w->device == d && w->slot == sl);
+            if (found) continue;
+            Worker *w = new Worker();
+            w->device = d;
+            w->slot = sl;
+            int rc = bzap_ctx_create(d, &w->ctx);
+            if (rc != BZAP_OK) { delete w; cudaSetDevice(cur); return rc; }
+            w->th = std::thread(worker_main, E, w);
+            w->th.detach();
+            E->workers.push_back(w);
+        }
+    cudaSetDevice(cur);
+    BatchJob job;
+    job.fn = std::move(fn);
+    job.order.resize(count);
+    for (int i = 0; i < count; ++i) job.order[i] = i;
+    if (sizes) std::stable_sort(job.order.begin(), job.order.end(), [&](int a, int b) { return sizes[a] > sizes[b]; });
+    job.dev_lo = dev_lo;
+    job.dev_hi = dev_hi;
+    job.n_streams = n_streams;
+    int part = 0;
+    for (Worker *w : E->workers) part += (w->device >= dev_lo && w->device < dev_hi && w->slot < n_streams);
+    {
+        std::unique_lock<std::mutex> lk(E->mu);
+        job.pending = part;
+        E->job = &job;
+        ++E->generation;
+        E->cv_work.notify_all();
+        E->cv_done.wait(lk, [&] { return job.pending == 0; });
+        E->job = nullptr;
     }
-    while ((int)g_pool.ctxs.size() < n_streams) {
-        bzap_ctx *c = nullptr;
-        int rc = bzap_ctx_create(dev, &c);
-        if (rc != BZAP_OK) return rc;
-        g_pool.ctxs.push_back(c);
-    }
-    std::atomic<int> next(0), first_err(BZAP_OK);
-    std::vector<std::thread> workers;
-    for (int w = 0; w < n_streams; ++w) {
-        workers.emplace_back([&, w]() {
-            bzap_ctx *c = g_pool.ctxs[w];
-            cudaSetDevice(c->device);
-            for (int i = next.fetch_add(1); i < count; i = next.fetch_add(1)) {
-                int rc = fn(c, i);
-                int ok = BZAP_OK;
-                if (rc != BZAP_OK) first_err.compare_exchange_strong(ok, rc);
-            }
-        });
-    }
-    for (auto &t : workers) t.join();
-    return first_err.load();
+    return job.first_err.load();
 }
+}   // namespace
 
-extern "C" int bzap_compress_batch(const uint8_t *const *ins, const size_t *ns, uint8_t *const *outs, size_t *out_lens,
-                                   int count, int n_streams)
+extern "C" int bzap_compress_batch_gpus(const uint8_t *const *ins, const size_t *ns, uint8_t *const *outs, size_t *out_lens,
+                                        int count, int n_gpus, int n_streams)
 {
     if (!ins || !ns || !outs || !out_lens) return BZAP_ERR_ARG;
-    return run_batch(count, n_streams, [&](bzap_ctx *c, int i) {
-        c->err[0] = 0;
+    return run_batch(count, ns, n_gpus, n_streams, [&](bzap_ctx *c, int i) {
         return compress_any(c, ins[i], false, ns[i], outs[i], false, bzap_compress_bound(ns[i]), &out_lens[i]);
     });
 }
-extern "C" int bzap_decompress_batch(const uint8_t *const *ins, const size_t *in_lens, uint8_t *const *outs,
-                                     size_t *out_lens, int count, int n_streams)
+extern "C" int bzap_decompress_batch_gpus(const uint8_t *const *ins, const size_t *in_lens, uint8_t *const *outs,
+                                          const size_t *out_caps, size_t *out_lens, int count, int n_gpus, int n_streams)
 {
-    if (!ins || !in_lens || !outs || !out_lens) return BZAP_ERR_ARG;
-    return run_batch(count, n_streams, [&](bzap_ctx *c, int i) {
-        c->err[0] = 0;
-        return decompress_any(c, ins[i], false, in_lens[i], outs[i], false,
-                              (size_t)bzap_decompressed_size(ins[i], in_lens[i]), &out_lens[i]);
+    if (!ins || !in_lens || !outs || !out_caps || !out_lens) return BZAP_ERR_ARG;
+    return run_batch(count, in_lens, n_gpus, n_streams, [&](bzap_ctx *c, int i) {
+        return decompress_any(c, ins[i], false, in_lens[i], outs[i], false, out_caps[i], &out_lens[i]);
     });
+}
+extern "C" int bzap_compress_batch(const uint8_t *const *ins, const size_t *ns, uint8_t *const *outs, size_t *out_lens,
+                                   int count, int n_streams)
+{
+    return bzap_compress_batch_gpus(ins, ns, outs, out_lens, count, 0, n_streams);
+}
+extern "C" int bzap_decompress_batch(const uint8_t *const *ins, const size_t *in_lens, uint8_t *const *outs,
+                                     const size_t *out_caps, size_t *out_lens, int count, int n_streams)
+{
+    return bzap_decompress_batch_gpus(ins, in_lens, outs, out_caps, out_lens, count, 0, n_streams);
+}
+
+// the reference's file loop (main.cpp:424-437) over n_gpus devices: in_paths[i] -> out_paths[i]
+static int batch_files(const char *const *in_paths, const char *const *out_paths, int count, int n_gpus, int n_streams, bool comp)
+{
+    if (!in_paths || !out_paths) return BZAP_ERR_ARG;
+    std::vector<size_t> sizes(count > 0 ? count : 0, 0);
+    for (int i = 0; i < count; ++i) {
+        if (!in_paths[i] || !out_paths[i]) return BZAP_ERR_ARG;
+        FILE *f = fopen(in_paths[i], "rb");
+        if (f) { fseek(f, 0, SEEK_END); long sz = ftell(f); fclose(f); sizes[i] = sz > 0 ? (size_t)sz : 0; }
+    }
+    return run_batch(count, sizes.data(), n_gpus, n_streams, [&](bzap_ctx *c, int i) {
+        return comp ? bzap_compress_file(c, in_paths[i], out_paths[i]) : bzap_decompress_file(c, in_paths[i], out_paths[i]);
+    });
+}
+extern "C" int bzap_compress_files(const char *const *in_paths, const char *const *out_paths, int count, int n_gpus, int n_streams)
+{
+    return batch_files(in_paths, out_paths, count, n_gpus, n_streams, true);
+}
+extern "C" int bzap_decompress_files(const char *const *in_paths, const char *const *out_paths, int count, int n_gpus, int n_streams)
+{
+    return batch_files(in_paths, out_paths, count, n_gpus, n_streams, false);
 }
 
 // ---- stage level ------------------------------------------------------------------------------------------

@@ -111,13 +111,27 @@ int      bzap_decompress(bzap_ctx *ctx, const uint8_t *in, size_t in_len, uint8_
 int bzap_compress_device(bzap_ctx *ctx, const uint8_t *d_in, size_t n, uint8_t *d_out, size_t out_cap, size_t *out_len);
 int bzap_decompress_device(bzap_ctx *ctx, const uint8_t *d_in, size_t in_len, uint8_t *d_out, size_t out_cap, size_t *out_len);
 
-/* ---- batch: independent files, one BWT block each (main.cpp:424-437 loop) ------------------ */
-/* compresses count host buffers; outs[i] needs bzap_compress_bound(ns[i]) bytes.  Files are
- * spread over n_streams internal contexts of the current device (0 = default 4).           */
+/* ---- batch: independent files, one BWT block each (the reference's 14-file loop, main.cpp:424-437) ----
+ * Files are handed out largest first to a persistent pool of workers (one context = one stream + scratch
+ * per worker), n_streams per device (0 = default 4), so that on every device the host-to-device copy of one
+ * file and the read-back of another overlap the kernels of a third (pinned host buffers make the copies
+ * asynchronous).  outs[i] needs bzap_compress_bound(ns[i]) bytes.  Returns the first error, if any.
+ *   ..._batch       the current CUDA device
+ *   ..._batch_gpus  devices 0 .. n_gpus-1 of this process, greedy largest-first over all their workers
+ *   ..._files       the same for paths: in_paths[i] -> out_paths[i] (read_bytes / write_bytes,
+ *                   io_utilities.h:7-55); n_gpus = 0 means the current device                          */
 int bzap_compress_batch(const uint8_t *const *ins, const size_t *ns, uint8_t *const *outs, size_t *out_lens,
                         int count, int n_streams);
-int bzap_decompress_batch(const uint8_t *const *ins, const size_t *in_lens, uint8_t *const *outs, size_t *out_lens,
-                          int count, int n_streams);
+/* outs[i] holds out_caps[i] bytes (size it with bzap_decompressed_size); a header that asks for more
+ * fails with BZAP_ERR_CAPACITY instead of overrunning the buffer                                       */
+int bzap_decompress_batch(const uint8_t *const *ins, const size_t *in_lens, uint8_t *const *outs, const size_t *out_caps,
+                          size_t *out_lens, int count, int n_streams);
+int bzap_compress_batch_gpus(const uint8_t *const *ins, const size_t *ns, uint8_t *const *outs, size_t *out_lens,
+                             int count, int n_gpus, int n_streams);
+int bzap_decompress_batch_gpus(const uint8_t *const *ins, const size_t *in_lens, uint8_t *const *outs, const size_t *out_caps,
+                               size_t *out_lens, int count, int n_gpus, int n_streams);
+int bzap_compress_files(const char *const *in_paths, const char *const *out_paths, int count, int n_gpus, int n_streams);
+int bzap_decompress_files(const char *const *in_paths, const char *const *out_paths, int count, int n_gpus, int n_streams);
 
 /* ---- stage level (host pointers), one per SURVEY 8a row ------------------------------------- */
 /* bwt()                   main.cpp:77-91 with bwt_cmp_straight :46-59                         */

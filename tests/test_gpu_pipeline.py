@@ -2,6 +2,7 @@
 goldens + the oracle), cross-decoding with the real reference binaries when oracle/_ref
 travelled with the snapshot, round trips at BASELINE.json's full sizes."""
 import hashlib
+import json
 import os
 import subprocess
 
@@ -279,3 +280,51 @@ def test_text_256m_roundtrip_property():
     m = ctx.decompress_ptr(out.data_ptr(), fl, back.data_ptr(), n, device=True)
     assert m == n and bool(torch.equal(back, x))
     ctx.close()
+
+
+def test_batch_over_gpus_and_files(tmp_path):
+    """bzap_compress_batch_gpus / bzap_compress_files: the 14-file loop (main.cpp:424-437) handed out largest
+    first over the workers of n_gpus devices; every file equals its reference golden."""
+    import torch
+    from bwt_mtf_huffman_compressor_b200 import workloads as W
+    cal = W.calgary()
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))["calgary"]
+    n_gpus = min(torch.cuda.device_count(), 2)
+    datas = [cal[n] for n in W.CALGARY_FILES]
+    blobs = bz.compress_batch(datas, n_streams=3, n_gpus=n_gpus)
+    for name, b in zip(W.CALGARY_FILES, blobs):
+        assert hashlib.sha256(b.tobytes()).hexdigest() == g[name]["sha256"], name
+    outs = bz.decompress_batch(blobs, n_streams=3, n_gpus=n_gpus)
+    for name, o in zip(W.CALGARY_FILES, outs):
+        assert o.tobytes() == cal[name], name
+    ins, encs, decs = [], [], []
+    for name in W.CALGARY_FILES:
+        p = tmp_path / name
+        p.write_bytes(cal[name])
+        ins.append(str(p)); encs.append(str(p) + ".bz"); decs.append(str(p) + ".out")
+    bz.compress_files(ins, encs, n_gpus=n_gpus, n_streams=2)
+    bz.decompress_files(encs, decs, n_gpus=n_gpus, n_streams=2)
+    for name, e, d in zip(W.CALGARY_FILES, encs, decs):
+        assert hashlib.sha256(open(e, "rb").read()).hexdigest() == g[name]["sha256"], name
+        assert open(d, "rb").read() == cal[name], name
+    # a corrupt header must not overrun the caller's buffer (out_caps)
+    bad = blobs[0].copy()
+    bad[8:16] = np.frombuffer(np.array([len(cal["bib"]) + 1000], dtype="<u8").tobytes(), dtype=np.uint8)
+    with pytest.raises(bz.BzapError):
+        bz._batch(False, [bad], [len(cal["bib"])], 1, 0)
+
+
+def test_contexts_on_two_devices_in_one_process():
+    """per-device kernel attributes: a second context on another GPU of the same process must work"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from bwt_mtf_huffman_compressor_b200 import workloads as W
+    d = W.synthetic_text(3 << 20)
+    want = O.o_compress(d)
+    for dev in (0, 1, 0):
+        c = bz.Context(dev)
+        blob = bz.compress_bytes(d, c)
+        assert np.array_equal(blob, want)
+        assert np.array_equal(bz.decompress_bytes(blob, c), d)
+        c.close()
