@@ -152,12 +152,12 @@ void *arena_alloc(bzap_ctx *ctx, size_t bytes)
 size_t scratch_bytes_compress(size_t n)
 {
     // text, last column, mtf, file image | 2 x u64 keys, 2 x u32 payload, rank | sort + mtf tables
-    return 4 * (n + 1024) + 33 * n + sort_scratch_bytes((u32)n) + 2 * (n / 128 + 4096) * 1280 + (8u << 20);
+    return 4 * (n + 1024) + 33 * n + sort_scratch_bytes((u32)n) + 2 * mtf_scratch_bytes(n) + (8u << 20);
 }
 size_t scratch_bytes_decompress(size_t n, size_t payload)
 {
     // payload copy, mtf, last column, out | T | sort status | mtf tables | decode state
-    return (payload + 4096) + 3 * (n + 1024) + 5 * n + sort_scratch_bytes((u32)n) + 2 * (n / 128 + 4096) * 768 +
+    return (payload + 4096) + 3 * (n + 1024) + 5 * n + sort_scratch_bytes((u32)n) + 2 * mtf_scratch_bytes(n) +
            (payload / 128 + 4096) * 32 + (8u << 20) +
            (n <= (2u << 20) ? 36 * n : 0);         // small blocks: 8-row splitter buckets in ibwt.cu (IB_SMALL_N)
 }

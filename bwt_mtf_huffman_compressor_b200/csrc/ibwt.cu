@@ -13,10 +13,12 @@
 //      blocks use 64-row buckets; small ones (latency bound: the longest sub-list, ~ stride x ln(nodes)
 //      dependent loads, is what the walk waits for) use 8-row buckets;
 //   2. ibwt_walk_len_kernel : every splitter walks T until it lands on the next splitter ->
-//      reduced list (next splitter, sublist length);
+//      reduced list (next splitter, sublist length), emitting its bytes into a 256-byte slot on the way;
+//      a sub-list that fills its slot continues as a NEW node appended to the reduced list, so no
+//      sub-list is longer than a slot;
 //   3. ibwt_wyllie_kernel   : pointer jumping on the reduced list, cut open at `primary`, gives
 //      every splitter on primary's cycle its distance to the end, hence its output offset;
-//   4. ibwt_walk_write_kernel: every reachable splitter walks again and writes its bytes;
+//   4. ibwt_copy_slots_kernel: every reachable node copies its slot to its place in the output;
 //   5. ibwt_extend_kernel   : out[i] = out[i mod cycle_length] when the cycle is shorter than N.
 // Nothing assumes a single list, so splitters on other cycles are simply never reached.
 #include "device_common.cuh"
@@ -94,12 +96,14 @@ __device__ __forceinline__ u32 ib_first_col(const FirstCol &F, u32 r)
 // of sub-lists is exhausted.
 // The walk already visits every row once, so it also emits the output bytes F(row) -- into a
 // fixed slot of IB_SLOT bytes per sub-list, because the sub-list's place in the output is only
-// known after the ranking.  Sub-lists longer than a slot remember where to resume.
+// known after the ranking.  A sub-list that fills its slot (geometric lengths, mean = the stride: ~2 % of
+// them at a stride of 64) hands over to a fresh node taken from an atomic counter (counter[1]); that node
+// is only ever reached through its predecessor's link, never looked up by row.
 #define IB_REFILL 8
 #define IB_SLOT 256
 __global__ void __launch_bounds__(256)
 ibwt_walk_len_kernel(const u32 *__restrict__ T, u32 n, u32 nb, u32 slog, u32 primary, const u32 *__restrict__ cum,
-                     u64 *__restrict__ node, u8 *__restrict__ slots, u32 *__restrict__ resume, u32 *counter)
+                     u64 *__restrict__ node, u8 *__restrict__ slots, u32 node_cap, u32 *counter)
 {
     __shared__ FirstCol F;
     ib_first_col_init(F, cum, n);
@@ -125,8 +129,20 @@ ibwt_walk_len_kernel(const u32 *__restrict__ T, u32 n, u32 nb, u32 slog, u32 pri
             exhausted = base + want > nb;
         }
         if (j != IB_NIL) {
-            if (len < IB_SLOT) slots[(size_t)j * IB_SLOT + len] = (u8)ib_first_col(F, row);   // out[i] = F(x_i), main.cpp:71
-            else if (len == IB_SLOT) resume[j] = row;
+            if (len == IB_SLOT) {                            // slot full: the rest of the sub-list becomes a node of its own
+                const u32 nj = nb + 1u + atomicAdd(counter + 1, 1u);
+                if (nj < node_cap) {
+                    node[j] = ((u64)nj << 32) | IB_SLOT;
+                    j = nj;
+                    len = 0;
+                } else {
+                    atomicExch(counter + 2, 1u);             // cannot happen with node_cap = 5/4 of the splitters; reported
+                    node[j] = ((u64)IB_NIL << 32) | IB_SLOT;
+                    j = IB_NIL;
+                    continue;
+                }
+            }
+            slots[(size_t)j * IB_SLOT + len] = (u8)ib_first_col(F, row);   // out[i] = F(x_i), main.cpp:71
             row = T[row];
             ++len;
             u32 nx = ib_node_of(row, n, nb, primary, slog);
@@ -140,10 +156,12 @@ ibwt_walk_len_kernel(const u32 *__restrict__ T, u32 n, u32 nb, u32 slog, u32 pri
 }
 
 // one pointer-jumping round: dist[j] += dist[next[j]]; next[j] = next[next[j]]
-__global__ void __launch_bounds__(256) ibwt_wyllie_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, u32 count)
+// (nodes = the splitters, `primary`, and however many continuation nodes the walk appended: counter[1])
+__global__ void __launch_bounds__(256)
+ibwt_wyllie_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, u32 base_nodes, const u32 *__restrict__ counter)
 {
     const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= count) return;
+    if (j >= base_nodes + counter[1]) return;
     u64 a = in[j];
     u32 nx = (u32)(a >> 32);
     if (nx != IB_NIL) {
@@ -157,39 +175,17 @@ __global__ void __launch_bounds__(256) ibwt_wyllie_kernel(const u64 *__restrict_
 // cycle_len = dist[nb] bytes, so sub-list j belongs at out[cycle_len - dist[j] ...].
 // One warp per sub-list copies its slot; sub-lists on other cycles never reach `primary` and are skipped.
 __global__ void __launch_bounds__(256)
-ibwt_copy_slots_kernel(u32 nb, const u64 *__restrict__ len_node, const u64 *__restrict__ ranked,
+ibwt_copy_slots_kernel(u32 nb, const u32 *__restrict__ counter, const u64 *__restrict__ len_node, const u64 *__restrict__ ranked,
                        const u8 *__restrict__ slots, u8 *__restrict__ out)
 {
     const u32 j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
-    if (j > nb) return;
+    if (j > nb + counter[1]) return;
     const u64 rk = ranked[j];
     if ((u32)(rk >> 32) != IB_NIL) return;
     const u32 len = min((u32)len_node[j], (u32)IB_SLOT);
     const u32 o = (u32)ranked[nb] - (u32)rk;
     const u8 *src = slots + (size_t)j * IB_SLOT;
     for (u32 t = lane; t < len; t += 32) out[o + t] = src[t];
-}
-
-// the few sub-lists longer than a slot walk on from where the first walk left the slot
-__global__ void __launch_bounds__(256)
-ibwt_overflow_kernel(const u32 *__restrict__ T, u32 n, u32 nb, const u64 *__restrict__ len_node,
-                     const u64 *__restrict__ ranked, const u32 *__restrict__ resume, const u32 *__restrict__ cum,
-                     u8 *__restrict__ out)
-{
-    __shared__ FirstCol F;
-    ib_first_col_init(F, cum, n);
-    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j > nb) return;
-    const u32 len = (u32)len_node[j];
-    if (len <= IB_SLOT) return;
-    const u64 rk = ranked[j];
-    if ((u32)(rk >> 32) != IB_NIL) return;
-    u32 o = (u32)ranked[nb] - (u32)rk + IB_SLOT;
-    u32 row = resume[j];
-    for (u32 t = IB_SLOT; t < len; ++t) {
-        out[o++] = (u8)ib_first_col(F, row);
-        row = T[row];
-    }
 }
 
 __global__ void __launch_bounds__(256) ibwt_extend_kernel(u8 *out, u32 n, u32 cycle_len)
@@ -207,29 +203,29 @@ int dev_ibwt(bzap_ctx *ctx, const u8 *d_last, size_t n64, u64 primary64, u8 *d_o
     const u32 n = (u32)n64, primary = (u32)primary64;
     const u32 slog = n <= IB_SMALL_N ? IB_STRIDE_LOG_SMALL : IB_STRIDE_LOG_LARGE;
     const u32 nb = (u32)(((u64)n + (1u << slog) - 1) >> slog);
-    const u32 nodes = nb + 1;
+    const u32 base_nodes = nb + 1;
+    const u32 nodes = base_nodes + base_nodes / 4 + 1024;        // room for the continuation nodes of full slots
     u32 *d_T = arena_get<u32>(ctx, n);
     u32 *d_cum = arena_get<u32>(ctx, 260);
     u64 *d_len = arena_get<u64>(ctx, nodes);
     u64 *d_rank[2] = {arena_get<u64>(ctx, nodes), arena_get<u64>(ctx, nodes)};
     u32 *d_work = arena_get<u32>(ctx, 8);
     u8 *d_slots = arena_get<u8>(ctx, (size_t)nodes * IB_SLOT);
-    u32 *d_resume = arena_get<u32>(ctx, nodes);
-    if (!d_T || !d_cum || !d_len || !d_rank[0] || !d_rank[1] || !d_work || !d_slots || !d_resume)
+    if (!d_T || !d_cum || !d_len || !d_rank[0] || !d_rank[1] || !d_work || !d_slots)
         return bzap_fail(ctx, BZAP_ERR_NOMEM, "ibwt scratch");
     CU(ctx, cudaMemsetAsync(d_work, 0, 8 * sizeof(u32), ctx->stream));
-    const u32 wgrid = nodes / 256 + 1 < 148u * 8u ? nodes / 256 + 1 : 148u * 8u;
+    const u32 wgrid = base_nodes / 256 + 1 < 148u * 8u ? base_nodes / 256 + 1 : 148u * 8u;
     RET(dev_sort_positions_by_byte(ctx, d_last, n, d_T, d_cum));
     const u32 nblk = (nodes + 255) / 256;
     CU(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
-    LAUNCH(ctx, ibwt_walk_len_kernel, wgrid, 256, 0, d_T, n, nb, slog, primary, d_cum, d_len, d_slots, d_resume, d_work);
+    LAUNCH(ctx, ibwt_walk_len_kernel, wgrid, 256, 0, d_T, n, nb, slog, primary, d_cum, d_len, d_slots, nodes, d_work);
     CU(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
     ctx->stats.walk_bytes = 5ull * n;            // T[row] (4 B) read + one slot byte written per row
     // pointer jumping: after r rounds every node has jumped 2^r links
     int cur = 0;
     const u64 *src = d_len;
     for (u64 span = 1; span < nodes; span <<= 1) {
-        LAUNCH(ctx, ibwt_wyllie_kernel, nblk, 256, 0, src, d_rank[cur], nodes);
+        LAUNCH(ctx, ibwt_wyllie_kernel, nblk, 256, 0, src, d_rank[cur], base_nodes, d_work);
         src = d_rank[cur];
         cur ^= 1;
     }
@@ -237,11 +233,12 @@ int dev_ibwt(bzap_ctx *ctx, const u8 *d_last, size_t n64, u64 primary64, u8 *d_o
         CU(ctx, cudaMemcpyAsync(d_rank[0], d_len, nodes * sizeof(u64), cudaMemcpyDeviceToDevice, ctx->stream));
         src = d_rank[0];
     }
-    LAUNCH(ctx, ibwt_copy_slots_kernel, (u32)(((size_t)nodes * 32 + 255) / 256), 256, 0, nb, d_len, src, d_slots, d_out);
-    LAUNCH(ctx, ibwt_overflow_kernel, nblk, 256, 0, d_T, n, nb, d_len, src, d_resume, d_cum, d_out);
+    LAUNCH(ctx, ibwt_copy_slots_kernel, (u32)(((size_t)nodes * 32 + 255) / 256), 256, 0, nb, d_work, d_len, src, d_slots, d_out);
     u64 *h_cycle = (u64 *)(ctx->mailbox + 1056);
     CU(ctx, cudaMemcpyAsync(h_cycle, src + nb, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(h_cycle + 1, d_work, 4 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (((const u32 *)(h_cycle + 1))[2]) return bzap_fail(ctx, BZAP_ERR_CUDA, "list ranking ran out of continuation nodes");
     const u32 cycle_len = (u32)*h_cycle;
     if ((u32)(*h_cycle >> 32) != IB_NIL || cycle_len == 0 || cycle_len > n)
         return bzap_fail(ctx, BZAP_ERR_CUDA, "list ranking failed (cycle %u)", cycle_len);
