@@ -165,8 +165,8 @@ def run_ours(args):
     h_backs = [h_back] + [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in range(EB - 1)]
 
     def step_host():
-        fls = bz.batch_ptrs(True, [t.data_ptr() for t in h_ins], [n] * EB, [t.data_ptr() for t in h_files], None, n_streams=2)
-        bz.batch_ptrs(False, [t.data_ptr() for t in h_files], fls, [t.data_ptr() for t in h_backs], [n] * EB, n_streams=2)
+        fls = bz.batch_ptrs(True, [t.data_ptr() for t in h_ins], [n] * EB, [t.data_ptr() for t in h_files], None, n_streams=args.e2e_streams)
+        bz.batch_ptrs(False, [t.data_ptr() for t in h_files], fls, [t.data_ptr() for t in h_backs], [n] * EB, n_streams=args.e2e_streams)
         return fls[0]
 
     for _ in range(max(args.warmup, 3)):
@@ -272,7 +272,7 @@ def run_ours(args):
             "e2e": {"value": round(e2e, 2), "unit": UNIT, "h2d_bytes_per_step": int(n + fl) * args.e2e_blocks,
                     "d2h_bytes_per_step": int(fl + n) * args.e2e_blocks, "ms_per_step": round(host_ms / K, 4),
                     "blocks_per_step": args.e2e_blocks, "ms_per_block": round(host_ms / K / args.e2e_blocks, 4),
-                    "api": "bzap_compress_batch_gpus + bzap_decompress_batch_gpus, pinned host buffers, 2 workers per GPU "
+                    "api": "bzap_compress_batch_gpus + bzap_decompress_batch_gpus, pinned host buffers, %d workers per GPU " % args.e2e_streams +
                            "(H2D / D2H of one block overlap the kernels of another)"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "onesweep_pass_kernel<u64 key, u32 payload> (BWT prefix-doubling sort pass over all N rotations)",
@@ -511,6 +511,7 @@ def main():
     ap.add_argument("--no-block1g", action="store_true", help="skip the single 1 GiB block (profiling runs)")
     ap.add_argument("--block-size", type=int, default=1 << 30)
     ap.add_argument("--e2e-blocks", type=int, default=4, help="blocks per e2e step (batch entry points)")
+    ap.add_argument("--e2e-streams", type=int, default=4, help="workers (streams) per GPU for the e2e batch")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
