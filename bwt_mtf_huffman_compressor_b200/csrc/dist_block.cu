@@ -197,20 +197,76 @@ __global__ void dist_sample_keys_kernel(const u8 *__restrict__ text, u32 n, u32 
     keys[j] = k;
 }
 
-// bytes tile_base .. tile_base + DB_TILE + 7 (cyclic) of the text into shared memory
-__device__ __forceinline__ void dist_stage_tile(const u8 *__restrict__ text, u32 n, u32 tile_base, u8 *sb)
+// ---- streaming the text through shared memory: 1-D bulk copies (TMA engine) on an mbarrier pipeline ----------
+// Both text sweeps give every block a contiguous range of 2 KiB tiles.  One elected thread issues
+// cp.async.bulk for tile t+1 into the other of two buffers while the block computes the windows of tile t;
+// the copy completes on that buffer's mbarrier (expect_tx / try_wait.parity), so nobody spends instructions
+// on the staging and the load latency hides behind the previous tile.  Tiles that wrap around the end of
+// the text, or a text that is not 16-byte aligned, are staged by hand.
+struct TileStream {
+    __align__(16) u8 buf[2][DB_TILE + 16];
+    unsigned long long bar[2];
+};
+__device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, u32 count)
 {
-    if ((u64)tile_base + DB_TILE + 8 <= n && (reinterpret_cast<uintptr_t>(text) & 15u) == 0) {
-        if (threadIdx.x < DB_TILE / 16)
-            reinterpret_cast<uint4 *>(sb)[threadIdx.x] = reinterpret_cast<const uint4 *>(text + tile_base)[threadIdx.x];
-        if (threadIdx.x >= DB_BLOCK - 8) sb[DB_TILE + (threadIdx.x - (DB_BLOCK - 8))] = text[tile_base + DB_TILE + (threadIdx.x - (DB_BLOCK - 8))];
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, u32 phase)
+{
+    u32 done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(smem_addr(bar)), "r"(phase)
+                     : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ bool tile_is_bulk(const u8 *text, u32 n, u32 tile)
+{
+    return (u64)tile * DB_TILE + DB_TILE + 16 <= n && (reinterpret_cast<uintptr_t>(text) & 15u) == 0;
+}
+// called by ONE thread, after a block barrier that retired every read of `buf`
+__device__ __forceinline__ void tile_issue(TileStream &TS, u32 b, const u8 *text, u32 tile)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // earlier generic-proxy accesses of the buffer first
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&TS.bar[b])), "r"((u32)(DB_TILE + 16)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(TS.buf[b])),
+                 "l"(text + (size_t)tile * DB_TILE), "r"((u32)(DB_TILE + 16)), "r"(smem_addr(&TS.bar[b]))
+                 : "memory");
+}
+__device__ __forceinline__ void tile_stream_begin(TileStream &TS, const u8 *text, u32 n, u32 t0, u32 t1)
+{
+    if (threadIdx.x == 0) {
+        mbar_init(&TS.bar[0], 1);
+        mbar_init(&TS.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && t0 < t1 && tile_is_bulk(text, n, t0)) tile_issue(TS, 0, text, t0);
+}
+// makes tile `tile` available in TS.buf[b] (b = parity of tile - t0) and starts the copy of the next one;
+// `phases` (bit b = phase of barrier b) is uniform over the block.  The caller ends the iteration with
+// __syncthreads() so that the buffer can be refilled.
+__device__ __forceinline__ const u32 *tile_stream_get(TileStream &TS, const u8 *text, u32 n, u32 tile, u32 t0, u32 t1, u32 &phases)
+{
+    const u32 b = (tile - t0) & 1u;
+    if (threadIdx.x == 0 && tile + 1 < t1 && tile_is_bulk(text, n, tile + 1)) tile_issue(TS, b ^ 1u, text, tile + 1);
+    if (tile_is_bulk(text, n, tile)) {
+        mbar_wait(&TS.bar[b], (phases >> b) & 1u);
+        phases ^= 1u << b;
     } else {
+        const u32 tile_base = tile * DB_TILE;
         for (u32 i = threadIdx.x; i < DB_TILE + 8; i += DB_BLOCK) {
             u64 p = (u64)tile_base + i;
-            if (p >= n) p %= n;
-            sb[i] = text[p];
+            if (p >= n) p %= n;                    // cyclic window (main.cpp:38-44)
+            TS.buf[b][i] = text[p];
         }
+        __syncthreads();
     }
+    return reinterpret_cast<const u32 *>(TS.buf[b]);
 }
 // big-endian 8-byte window starting at byte o of the staged tile
 __device__ __forceinline__ u64 dist_window(const u32 *sw, u32 o)
@@ -230,17 +286,15 @@ __global__ void __launch_bounds__(DB_BLOCK)
 dist_owner_count_kernel(const u8 *__restrict__ text, u32 n, u64 lo_key, u64 hi_key, int hi_open, u32 tiles, u32 *counts,
                         u32 *__restrict__ range_cnt)
 {
-    __shared__ __align__(16) u8 sb[DB_TILE + 16];
+    __shared__ TileStream TS;
     __shared__ u32 s_tmp[40];
     const u32 tpb = (tiles + gridDim.x - 1) / gridDim.x;
-    const u32 t0 = blockIdx.x * tpb, t1 = min(tiles, t0 + tpb);
-    u32 below = 0, mine = 0;
+    const u32 t0 = min(tiles, blockIdx.x * tpb), t1 = min(tiles, t0 + tpb);
+    u32 below = 0, mine = 0, phases = 0;
+    tile_stream_begin(TS, text, n, t0, t1);
     for (u32 tile = t0; tile < t1; ++tile) {
         const u32 base = tile * DB_TILE;
-        __syncthreads();
-        dist_stage_tile(text, n, base, sb);
-        __syncthreads();
-        const u32 *sw = reinterpret_cast<const u32 *>(sb);
+        const u32 *sw = tile_stream_get(TS, text, n, tile, t0, t1, phases);
 #pragma unroll
         for (int i = 0; i < DB_ITEMS; ++i) {
             u32 o = threadIdx.x + i * DB_BLOCK;
@@ -250,6 +304,7 @@ dist_owner_count_kernel(const u8 *__restrict__ text, u32 n, u64 lo_key, u64 hi_k
                 mine += k >= lo_key && (hi_open || k < hi_key);
             }
         }
+        __syncthreads();
     }
     u32 tb, tm;
     block_exclusive_sum(below, s_tmp, &tb);
@@ -266,22 +321,21 @@ __global__ void __launch_bounds__(DB_BLOCK)
 dist_select_kernel(const u8 *__restrict__ text, u32 n, u64 lo_key, u64 hi_key, int hi_open, u32 tiles,
                    const u32 *__restrict__ range_cnt, u64 *__restrict__ keys, u32 *__restrict__ starts, u32 *hist8)
 {
-    __shared__ __align__(16) u8 sb[DB_TILE + 16];
+    __shared__ TileStream TS;
     __shared__ u32 s_h[8 * 256];
     __shared__ u32 s_tmp[40];
     for (u32 i = threadIdx.x; i < 8 * 256; i += DB_BLOCK) s_h[i] = 0;
     const u32 tpb = (tiles + gridDim.x - 1) / gridDim.x;
-    const u32 t0 = blockIdx.x * tpb, t1 = min(tiles, t0 + tpb);
+    const u32 t0 = min(tiles, blockIdx.x * tpb), t1 = min(tiles, t0 + tpb);
+    u32 phases = 0;
+    tile_stream_begin(TS, text, n, t0, t1);
     u32 part = 0;
     for (u32 b = threadIdx.x; b < blockIdx.x; b += DB_BLOCK) part += range_cnt[b];
     u32 out;
     block_exclusive_sum(part, s_tmp, &out);               // own rotations of all earlier ranges
     for (u32 tile = t0; tile < t1; ++tile) {
         const u32 base = tile * DB_TILE;
-        __syncthreads();
-        dist_stage_tile(text, n, base, sb);
-        __syncthreads();
-        const u32 *sw = reinterpret_cast<const u32 *>(sb);
+        const u32 *sw = tile_stream_get(TS, text, n, tile, t0, t1, phases);
         u64 k[DB_ITEMS];
         u32 keep = 0, cnt = 0;
 #pragma unroll
@@ -304,6 +358,7 @@ dist_select_kernel(const u8 *__restrict__ text, u32 n, u64 lo_key, u64 hi_key, i
 #pragma unroll
                 for (int p = 0; p < 8; ++p) atomicAdd(&s_h[p * 256 + ((u32)(k[i] >> (8 * p)) & 0xffu)], 1u);
             }
+        __syncthreads();                            // the tile's buffer may be refilled
     }
     __syncthreads();
     for (u32 i = threadIdx.x; i < 8 * 256; i += DB_BLOCK) {
