@@ -100,7 +100,7 @@ class ClockSampler:
 def run_ours(args):
     import torch
     import bwt_mtf_huffman_compressor_b200 as bz
-    from bwt_mtf_huffman_compressor_b200 import workloads as W
+    import workloads as W
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -470,7 +470,7 @@ def run_reference(args):
     each (single thread: the reference has no threading and cannot split a block).  One round trip
     costs about 90 s, so it is timed ONCE whatever --steps says (steps_measured = 1, no warm-up).
     The all-cores figure (independent 2 MiB slices, one process per core) is kept as an extra key."""
-    from bwt_mtf_huffman_compressor_b200 import workloads as W
+    import workloads as W
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:

@@ -230,7 +230,6 @@ int huff_decode_tables(const bzap_tree *t, DecodeTables *dt)
 {
     if (!tree_is_sane(t) || !dt) return BZAP_ERR_ARG;
     std::memset(dt, 0, sizeof *dt);
-    CodeTable ct;
     // depth (may exceed 64 for hostile files: the tables do not care)
     {
         std::vector<std::pair<int, int>> st(1, std::make_pair(t->root, 0));
@@ -244,7 +243,6 @@ int huff_decode_tables(const bzap_tree *t, DecodeTables *dt)
             st.push_back(std::make_pair(t->right[f.first], f.second + 1));
         }
     }
-    (void)ct;
     if (t->left[t->root] < 0) {
         dt->single_leaf = 1;
         dt->single_value = t->value[t->root];

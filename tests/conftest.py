@@ -21,7 +21,7 @@ def golden():
 
 @pytest.fixture(scope="session")
 def calgary():
-    from bwt_mtf_huffman_compressor_b200 import workloads
+    import workloads
     return workloads.calgary()
 
 

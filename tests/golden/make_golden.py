@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_lib as O  # noqa: E402
-from bwt_mtf_huffman_compressor_b200 import workloads as W  # noqa: E402
+import workloads as W  # noqa: E402
 
 
 def sha(a):

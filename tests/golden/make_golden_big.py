@@ -26,7 +26,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_lib as O  # noqa: E402
-from bwt_mtf_huffman_compressor_b200 import workloads as W  # noqa: E402
+import workloads as W  # noqa: E402
 
 OUT = os.path.join(HERE, "golden.json")
 BASE_SEED = 0x5EED0064

@@ -21,7 +21,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _inputs():
-    from bwt_mtf_huffman_compressor_b200 import workloads as W
+    import workloads as W
     rng = np.random.default_rng(8)
     rep = rng.integers(0, 256, 90000, dtype=np.uint8)
     rep[40000:43000] = rep[10000:13000]
@@ -133,7 +133,7 @@ def test_distributed_block_world8():
 def test_world1_in_process_matches_single_gpu_path():
     """same context type as every other entry point: no communicator = a world of one"""
     import bwt_mtf_huffman_compressor_b200 as bz
-    from bwt_mtf_huffman_compressor_b200 import workloads as W
+    import workloads as W
     d = W.synthetic_text(1 << 22)
     ctx = bz.Context(0)
     text = torch.from_numpy(d.copy()).cuda()

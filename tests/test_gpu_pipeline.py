@@ -11,7 +11,7 @@ import pytest
 
 import bwt_mtf_huffman_compressor_b200 as bz
 import oracle_lib as O
-from bwt_mtf_huffman_compressor_b200 import workloads as W
+import workloads as W
 from gpu_util import assert_same
 
 pytestmark = pytest.mark.gpu
@@ -286,7 +286,7 @@ def test_batch_over_gpus_and_files(tmp_path):
     """bzap_compress_batch_gpus / bzap_compress_files: the 14-file loop (main.cpp:424-437) handed out largest
     first over the workers of n_gpus devices; every file equals its reference golden."""
     import torch
-    from bwt_mtf_huffman_compressor_b200 import workloads as W
+    import workloads as W
     cal = W.calgary()
     g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))["calgary"]
     n_gpus = min(torch.cuda.device_count(), 2)
@@ -319,7 +319,7 @@ def test_contexts_on_two_devices_in_one_process():
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
-    from bwt_mtf_huffman_compressor_b200 import workloads as W
+    import workloads as W
     d = W.synthetic_text(3 << 20)
     want = O.o_compress(d)
     for dev in (0, 1, 0):

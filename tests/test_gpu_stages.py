@@ -5,7 +5,7 @@ import pytest
 
 import bwt_mtf_huffman_compressor_b200 as bz
 import oracle_lib as O
-from bwt_mtf_huffman_compressor_b200 import workloads as W
+import workloads as W
 from gpu_util import assert_same
 
 pytestmark = pytest.mark.gpu

@@ -11,7 +11,7 @@ import pytest
 
 import bwt_mtf_huffman_compressor_b200 as bz
 import oracle_lib as O
-from bwt_mtf_huffman_compressor_b200 import workloads as W
+import workloads as W
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 

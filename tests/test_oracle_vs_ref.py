@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from bwt_mtf_huffman_compressor_b200 import workloads as W
+import workloads as W
 
 need_ref = pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
 SMALL = ["obj1", "progc", "paper1", "geo"]          # the reference's BWT is O(N^2 log N): keep it quick

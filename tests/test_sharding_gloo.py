@@ -14,7 +14,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from bwt_mtf_huffman_compressor_b200 import sharding, workloads as W  # noqa: E402
+from bwt_mtf_huffman_compressor_b200 import sharding  # noqa: E402
+import workloads as W  # noqa: E402
 
 
 def test_shard_files_is_a_balanced_partition():

@@ -14,7 +14,7 @@ import tarfile
 
 import numpy as np
 
-_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # repo root (this file lives in tests/)
 CALGARY_TAR = os.path.join(_ROOT, "tests", "data", "calgary.tar.xz")
 CALGARY_FILES = ["bib", "book1", "book2", "geo", "news", "obj1", "obj2", "paper1", "paper2",
                  "pic", "progc", "progl", "progp", "trans"]  # order of main.cpp:418-419

@@ -4,9 +4,10 @@ Launch with torchrun (N > 1) or plain python (N = 1); prints one JSON line on ra
   python -m torch.distributed.run --nproc-per-node N tools/bench_block.py --size 1073741824"""
 import argparse, hashlib, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np, torch, torch.distributed as dist
 import bwt_mtf_huffman_compressor_b200 as bz
-from bwt_mtf_huffman_compressor_b200 import workloads as W
+import workloads as W
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=1 << 30)

@@ -3,9 +3,10 @@
 library's own CUDA-event stats.  Used by tools/gpu_sweep.sh to compare kernel variants."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np, torch
 import bwt_mtf_huffman_compressor_b200 as bz
-from bwt_mtf_huffman_compressor_b200 import workloads as W
+import workloads as W
 
 tag = sys.argv[1] if len(sys.argv) > 1 else ""
 cases = {"text64m": W.synthetic_text(1 << 26)}

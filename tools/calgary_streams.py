@@ -1,8 +1,9 @@
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 import bwt_mtf_huffman_compressor_b200 as bz
-from bwt_mtf_huffman_compressor_b200 import workloads as W
+import workloads as W
 cal = W.calgary()
 datas = [np.frombuffer(cal[n], dtype=np.uint8) for n in W.CALGARY_FILES]
 for ns in (1, 2, 4, 8, 14):

@@ -2,9 +2,10 @@
 """Per-file latency of the Calgary corpus on one stream (host buffers), plus launches per file."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np, torch
 import bwt_mtf_huffman_compressor_b200 as bz
-from bwt_mtf_huffman_compressor_b200 import workloads as W
+import workloads as W
 ctx = bz.Context(0)
 cal = W.calgary()
 tot_c = tot_d = 0.0

@@ -2,9 +2,10 @@
 """BASELINE config 4: 16 MiB degenerate / periodic blocks -- compress and decompress time per kind."""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np, torch
 import bwt_mtf_huffman_compressor_b200 as bz
-from bwt_mtf_huffman_compressor_b200 import workloads as W
+import workloads as W
 n = 1 << 24
 ctx = bz.Context(0)
 rows = {}
