@@ -370,8 +370,8 @@ def calgary_batch(bz, W, rank, world, dist):
     g = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))["calgary"]
     ok = True
     blobs = []
-    tc = td = 0.0
-    reps = 5
+    tcs, tds = [], []
+    reps = 7
     for it in range(reps + 2):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -380,19 +380,21 @@ def calgary_batch(bz, W, rank, world, dist):
         outs = bz.decompress_batch(blobs, 8) if blobs else []
         t2 = time.perf_counter()
         if it >= 2:
-            tc += t1 - t0
-            td += t2 - t1
+            tcs.append(t1 - t0)
+            tds.append(t2 - t1)
         if it == 0:
             for i, b, o in zip(mine, blobs, outs):
                 ok = ok and hashlib.sha256(b.tobytes()).hexdigest() == g[names[i]]["sha256"] and o.tobytes() == cal[names[i]]
-    tc = sharding.max_over_ranks(tc, dist, "cuda")
-    td = sharding.max_over_ranks(td, dist, "cuda")
+    # median of the repetitions: the batch is launch bound (about 1500 driver calls in ~3 ms), so one
+    # descheduled host thread on a shared box doubles a single repetition
+    tc = sharding.max_over_ranks(float(np.median(tcs)), dist, "cuda")
+    td = sharding.max_over_ranks(float(np.median(tds)), dist, "cuda")
     ok = sharding.max_over_ranks(0.0 if ok else 1.0, dist, "cuda") == 0.0
-    total = float(sum(sizes)) * reps
+    total = float(sum(sizes))
     return {"files": len(names), "bytes": int(sum(sizes)), "streams_per_gpu": 8,
             "compress_MBps": round(total / tc / 1e6, 1), "decompress_MBps": round(total / td / 1e6, 1),
             "roundtrip_MBps": round(total / (tc + td) / 1e6, 1), "byte_identical_to_reference_goldens": bool(ok),
-            "timing": "host wall clock incl. H2D/D2H, max over ranks"}
+            "timing": "host wall clock incl. H2D/D2H, median of %d repetitions, max over ranks" % reps}
 
 
 # ---------------------------------------------------------------------------------------------------
