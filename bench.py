@@ -98,6 +98,11 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------------
 def run_ours(args):
+    # stdout carries exactly ONE line, the JSON result: anything a library prints there during the run
+    # (NCCL announces its version on the first communicator) is sent to stderr instead
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import bwt_mtf_huffman_compressor_b200 as bz
     import workloads as W
@@ -305,7 +310,8 @@ def run_ours(args):
                 pass
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(data)
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(result_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
 
@@ -512,7 +518,7 @@ def main():
     ap.add_argument("--no-calgary", action="store_true", help="skip the Calgary batch (profiling runs)")
     ap.add_argument("--no-block1g", action="store_true", help="skip the single 1 GiB block (profiling runs)")
     ap.add_argument("--block-size", type=int, default=1 << 30)
-    ap.add_argument("--e2e-blocks", type=int, default=4, help="blocks per e2e step (batch entry points)")
+    ap.add_argument("--e2e-blocks", type=int, default=8, help="blocks per e2e step (batch entry points)")
     ap.add_argument("--e2e-streams", type=int, default=4, help="workers (streams) per GPU for the e2e batch")
     args = ap.parse_args()
     if args.impl == "reference":
