@@ -394,6 +394,16 @@ dist_respond_kernel(const u64 *__restrict__ req, u32 cnt, const u32 *__restrict_
     for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += gridDim.x * blockDim.x)
         resp[j] = rank_home[(u32)(req[j] >> 32) - lo];
 }
+// the same for requests that travelled as bare positions (only the position crosses NVLink: r1 stays home)
+__global__ void __launch_bounds__(256)
+dist_respond_pos_kernel(const u32 *__restrict__ pos, u32 cnt, const u32 *__restrict__ rank_home, u32 lo, u32 *__restrict__ resp)
+{
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += gridDim.x * blockDim.x) resp[j] = rank_home[pos[j] - lo];
+}
+__global__ void __launch_bounds__(256) dist_request_pos_kernel(const u64 *__restrict__ req, u32 m, u32 *__restrict__ pos)
+{
+    for (u32 a = blockIdx.x * blockDim.x + threadIdx.x; a < m; a += gridDim.x * blockDim.x) pos[a] = (u32)(req[a] >> 32);
+}
 
 // sort keys of a round: (r1 << rshift) | r2, with their eight digit histograms
 __global__ void __launch_bounds__(256)
@@ -950,9 +960,11 @@ extern "C" int bzap_compress_block_distributed(bzap_ctx *ctx, const uint8_t *d_t
             total_req = 0;
             for (int s = 0; s < G; ++s) total_req += C.c[s][me];
             if (total_req > shard) return bzap_fail(ctx, BZAP_ERR_CUDA, "pull: %llu requests for a shard of %u", (unsigned long long)total_req, shard);
-            RET(alltoallv(X, bk, req_in, sizeof(u64), C, false, BUF_REQ_IN));
+            // only the positions travel (4 of the 8 request bytes); d_r2 is free until the answers arrive
+            if (M) LAUNCH(ctx, dist_request_pos_kernel, grid_1d(M, 256 * 4), 256, 0, bk, M, d_r2);
+            RET(alltoallv(X, d_r2, req_in, sizeof(u32), C, false, BUF_REQ_IN));
             pt.stop("pull.alltoall requests");
-            if (total_req) LAUNCH(ctx, dist_respond_kernel, grid_1d(total_req, 256 * 4), 256, 0, req_in, (u32)total_req, rank_home, lo, resp_out);
+            if (total_req) LAUNCH(ctx, dist_respond_pos_kernel, grid_1d(total_req, 256 * 4), 256, 0, (const u32 *)req_in, (u32)total_req, rank_home, lo, resp_out);
             pt.stop("pull.respond");
             RET(alltoallv(X, resp_out, d_r2, sizeof(u32), C, true, BUF_R2));
             pt.stop("pull.alltoall responses");
