@@ -248,11 +248,11 @@ def decompressed_size(blob):
 
 
 def decompress_bytes(blob, ctx=None):
-    c = _ctx(ctx)
     a = _u8(blob)
     n = decompressed_size(a)
     if n > (1 << 30):
         raise BzapError(ERR_TOO_LARGE, "header asks for %d bytes" % n)      # before allocating anything
+    c = _ctx(ctx)
     out = np.empty(max(n, 1), dtype=np.uint8)
     got = c.decompress_ptr(a.ctypes.data, a.size, out.ctypes.data, n)
     return out[:got].copy()

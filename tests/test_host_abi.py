@@ -148,6 +148,45 @@ def test_fails_loudly_without_cuda():
     assert bz.lib().bzap_compress(None, a.ctypes.data, 3, out.ctypes.data, 400, C.byref(ln)) == bz.ERR_CUDA
 
 
+def test_batch_and_distributed_entry_points_fail_loudly_without_cuda(tmp_path):
+    """no device: the batch engine and the distributed block report BZAP_ERR_CUDA / BZAP_ERR_ARG, nothing falls
+    back to the CPU; the communicator id needs NCCL but no GPU"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(bz.BzapError) as e:
+        bz.compress_batch([b"abc", b"defg"], n_streams=2)
+    assert e.value.code == bz.ERR_CUDA
+    with pytest.raises(bz.BzapError) as e:
+        bz.decompress_batch([bytes(30)], n_streams=1)
+    assert e.value.code == bz.ERR_CUDA
+    src = tmp_path / "in"
+    src.write_bytes(b"hello")
+    with pytest.raises(bz.BzapError) as e:
+        bz.compress_files([str(src)], [str(src) + ".bz"], n_gpus=1)
+    assert e.value.code == bz.ERR_CUDA
+    assert not (tmp_path / "in.bz").exists()
+    ln = C.c_size_t(7)
+    assert bz.lib().bzap_compress_block_distributed(None, None, 5, None, 0, C.byref(ln)) == bz.ERR_ARG
+    try:
+        cid = bz.comm_unique_id()
+    except bz.BzapError as err:                    # a host without libnccl.so.2: the rest of the library still loads
+        assert err.code == -9
+    else:
+        assert len(cid) == bz.COMM_ID_BYTES and any(cid)
+
+
+def test_header_that_asks_for_too_much_is_refused_before_allocating():
+    blob = np.zeros(40, dtype=np.uint8)
+    blob[8:16] = np.frombuffer(np.array([1 << 40], dtype="<u8").tobytes(), dtype=np.uint8)
+    with pytest.raises(bz.BzapError) as e:
+        bz.decompress_bytes(blob)
+    assert e.value.code == bz.ERR_TOO_LARGE
+    with pytest.raises(bz.BzapError) as e:
+        bz.decompress_batch([blob])
+    assert e.value.code == bz.ERR_TOO_LARGE
+
+
 def test_cli_argument_contract():
     # main.cpp:440-443: wrong argc prints the message without newline and returns 1
     for exe in ("bzap_compress", "bzap_decompress"):
