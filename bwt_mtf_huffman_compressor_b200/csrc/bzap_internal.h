@@ -33,6 +33,10 @@ struct bzap_ctx {
     void *comm = nullptr;               // ncclComm_t
     int world = 1, rank = 0;
     u8 *dist_host = nullptr;            // pinned staging for the small collectives
+    u8 *dist_dev = nullptr;             // 1 MiB of device memory that is never exported (sample keys, counts, barrier words)
+    u8 *dist_arena = nullptr;           // the arena of the distributed path: peers map it, so it is never the one the
+    size_t dist_arena_cap = 0;          // other entry points reallocate, and it only grows under the protocol in dist_block.cu
+    bool dist_had_peers = false;
     void *peers = nullptr;              // the other ranks' arenas mapped through CUDA IPC (dist_block.cu: PeerMap)
     bzap_dist_stats dstats = {};
     char err[256] = {0};

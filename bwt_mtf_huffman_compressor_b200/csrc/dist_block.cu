@@ -134,13 +134,25 @@ static void peers_close(bzap_ctx *ctx)
     ctx->peers = nullptr;
 }
 
+// Collective when the ranks have mapped each other's arenas: everybody closes its mappings, and only after
+// everybody has done so is any arena freed (freeing exported memory that is still mapped elsewhere is undefined).
 void dist_comm_release(bzap_ctx *ctx)
 {
     peers_close(ctx);
-    if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy((ncclComm_t)ctx->comm);
+    if (ctx->comm && g_nccl.ok) {
+        if (ctx->dist_had_peers && ctx->dist_dev) {
+            u32 *w = (u32 *)ctx->dist_dev;
+            if (g_nccl.AllReduce(w, w + 4, 1, ncclUint32, ncclSum, (ncclComm_t)ctx->comm, ctx->stream) == ncclSuccess)
+                cudaStreamSynchronize(ctx->stream);
+        }
+        g_nccl.CommDestroy((ncclComm_t)ctx->comm);
+    }
     ctx->comm = nullptr;
     ctx->world = 1;
     ctx->rank = 0;
+    ctx->dist_had_peers = false;
+    if (ctx->dist_arena) { cudaFree(ctx->dist_arena); ctx->dist_arena = nullptr; ctx->dist_arena_cap = 0; }
+    if (ctx->dist_dev) { cudaFree(ctx->dist_dev); ctx->dist_dev = nullptr; }
     if (ctx->dist_host) { cudaFreeHost(ctx->dist_host); ctx->dist_host = nullptr; }
 }
 
@@ -692,6 +704,7 @@ static int peers_setup(Xchg &X, const u64 offs[4])
             for (int i = 0; i < 4; ++i) X.peer_off[p][i] = hello[p].off[i];
         }
     X.p2p = ok;
+    if (ok) ctx->dist_had_peers = true;
     return BZAP_OK;
 }
 
@@ -758,6 +771,51 @@ static double ev_ms2(cudaEvent_t a, cudaEvent_t b)
 static void put_u64le(u8 *p, u64 v) { for (int i = 0; i < 8; ++i) p[i] = (u8)(v >> (8 * i)); }
 }   // namespace
 
+namespace {
+// the distributed path works in its own arena (ctx->dist_arena): swapped in for the duration of the call
+struct ArenaSwap {
+    bzap_ctx *ctx;
+    u8 *arena;
+    size_t cap, off;
+    explicit ArenaSwap(bzap_ctx *c) : ctx(c), arena(c->arena), cap(c->arena_cap), off(c->arena_off)
+    {
+        c->arena = c->dist_arena;
+        c->arena_cap = c->dist_arena_cap;
+        c->arena_off = 0;
+    }
+    ~ArenaSwap()
+    {
+        ctx->dist_arena = ctx->arena;
+        ctx->dist_arena_cap = ctx->arena_cap;
+        ctx->arena = arena;
+        ctx->arena_cap = cap;
+        ctx->arena_off = off;
+    }
+};
+
+// Grows the arena if needed.  Peers may have it mapped: if ANY rank has to reallocate, every rank first closes
+// its mappings, and nobody frees before everybody has closed.
+static int dist_reserve(bzap_ctx *ctx, const NcclApi *N, int G, size_t bytes)
+{
+    u32 *w = (u32 *)ctx->dist_dev;                 // [0] flag in, [4] flag out, [8] barrier in, [12] barrier out
+    u32 grow = bytes > ctx->arena_cap ? 1u : 0u;
+    if (G > 1) {
+        u32 *h = (u32 *)(ctx->dist_host + DIST_HOST_BYTES - 2048);
+        *h = grow;
+        CU(ctx, cudaMemcpyAsync(w, h, sizeof(u32), cudaMemcpyHostToDevice, ctx->stream));
+        NC(ctx, N->AllReduce(w, w + 4, 1, ncclUint32, ncclMax, (ncclComm_t)ctx->comm, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(h + 1, w + 4, sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (h[1]) {
+            peers_close(ctx);
+            NC(ctx, N->AllReduce(w + 8, w + 12, 1, ncclUint32, ncclSum, (ncclComm_t)ctx->comm, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    return arena_reserve(ctx, bytes);
+}
+}   // namespace
+
 extern "C" int bzap_compress_block_distributed(bzap_ctx *ctx, const uint8_t *d_text, size_t n64, uint8_t *d_out, size_t out_cap,
                                                size_t *out_len)
 {
@@ -773,6 +831,11 @@ extern "C" int bzap_compress_block_distributed(bzap_ctx *ctx, const uint8_t *d_t
     const u32 n = (u32)n64;
     *out_len = 0;
     if (!ctx->dist_host) CU(ctx, cudaMallocHost((void **)&ctx->dist_host, DIST_HOST_BYTES));
+    if (!ctx->dist_dev) {
+        CU(ctx, cudaMalloc((void **)&ctx->dist_dev, 1u << 20));
+        CU(ctx, cudaMemset(ctx->dist_dev, 0, 1u << 20));
+    }
+    ArenaSwap arena_swap(ctx);
     bzap_dist_stats &st = ctx->dstats;
     st = bzap_dist_stats{};
     st.world = G;
@@ -801,13 +864,13 @@ extern "C" int bzap_compress_block_distributed(bzap_ctx *ctx, const uint8_t *d_t
 
     // ---- 0. splitters + how many rotations are mine (first, small reservation) ---------------------------------
     const u32 S = DIST_SAMPLES_PER_RANK * (u32)G;
-    RET(arena_reserve(ctx, (size_t)S * 8 + (size_t)G * 4096 + (1u << 20)));
+    // scratch of this phase lives in ctx->dist_dev (1 MiB: 64 B of collective words, counts, range counts, sample keys)
     CU(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     u64 bound_lo = 0, bound_hi = 0;
     int hi_open = 1;
     if (G > 1) {
-        u64 *d_sk = arena_get<u64>(ctx, S);
-        if (!d_sk) return bzap_fail(ctx, BZAP_ERR_NOMEM, "splitter scratch");
+        u64 *d_sk = (u64 *)(ctx->dist_dev + 512 * 1024);
+        static_assert((size_t)DIST_SAMPLES_PER_RANK * DIST_MAX_WORLD * 8 <= 512 * 1024, "sample keys must fit their half of dist_dev");
         LAUNCH(ctx, dist_sample_keys_kernel, (S + 255) / 256, 256, 0, d_text, n, S, d_sk);
         std::vector<u64> sk(S);
         CU(ctx, cudaMemcpyAsync(ctx->dist_host, d_sk, (size_t)S * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -818,16 +881,15 @@ extern "C" int bzap_compress_block_distributed(bzap_ctx *ctx, const uint8_t *d_t
         bound_lo = me == 0 ? 0 : sk[((size_t)me * S) / G];
         if (me + 1 < G) { bound_hi = sk[((size_t)(me + 1) * S) / G]; hi_open = 0; }
     }
-    u32 *d_cnt = arena_get<u32>(ctx, 8);
-    if (!d_cnt) return bzap_fail(ctx, BZAP_ERR_NOMEM, "count scratch");
+    u32 *d_cnt = (u32 *)(ctx->dist_dev + 1024);
     CU(ctx, cudaMemsetAsync(d_cnt, 0, 8 * sizeof(u32), ctx->stream));
     const u32 text_tiles = (n + DB_TILE - 1) / DB_TILE;
     const u32 sel_grid = grid_1d(text_tiles, 1, 148 * 8);
     u32 base = 0, m = n;
     std::vector<u32> range_cnt(sel_grid);
     {
-        u32 *d_rc = arena_get<u32>(ctx, sel_grid);
-        if (!d_rc || (size_t)sel_grid * 4 + 64 > DIST_HOST_BYTES) return bzap_fail(ctx, BZAP_ERR_NOMEM, "count scratch");
+        u32 *d_rc = (u32 *)(ctx->dist_dev + 4096);
+        static_assert(148 * 8 * 4 + 4096 <= 512 * 1024, "range counts must fit dist_dev");
         LAUNCH(ctx, dist_owner_count_kernel, sel_grid, DB_BLOCK, 0, d_text, n, bound_lo, bound_hi, hi_open, text_tiles, d_cnt, d_rc);
         CU(ctx, cudaMemcpyAsync(ctx->dist_host, d_cnt, 2 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaMemcpyAsync(ctx->dist_host + 64, d_rc, (size_t)sel_grid * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -848,7 +910,7 @@ extern "C" int bzap_compress_block_distributed(bzap_ctx *ctx, const uint8_t *d_t
                         sort_scratch_bytes(m) + 4 * (mm + 1024) /* last column, mtf, piece */ +
                         (me == 0 ? 2 * bzap_compress_bound(n) : 0) /* file image, staged pieces */ + mtf_scratch_bytes(m) +
                         (size_t)m / 16 + (16u << 20);
-    RET(arena_reserve(ctx, need));
+    RET(dist_reserve(ctx, N, G, need));
     u64 *K0 = arena_get<u64>(ctx, mm), *K1 = arena_get<u64>(ctx, mm);
     u32 *SV0 = arena_get<u32>(ctx, mm), *SV1 = arena_get<u32>(ctx, mm);
     u32 *d_rs = arena_get<u32>(ctx, mm);

@@ -174,7 +174,11 @@ int bzap_huff_decode(bzap_ctx *ctx, const uint8_t *payload, size_t payload_len, 
  * only unsettled rotations pull rank[(i+k) mod N] from the rank that owns text position i+k
  * (request / response all-to-all over NVLink) and send their new ranks home; MTF start lists, the
  * Huffman statistics and the bit offsets of the payload pieces are exchanged by all-gather.
- * A context without a communicator is a world of one (same code, no NCCL needed).                  */
+ * A context without a communicator is a world of one (same code, no NCCL needed).
+ * All three calls, and bzap_ctx_destroy of a context that holds a communicator, are collective: every rank
+ * makes them in the same order.  An error on one rank (out of memory, a failed collective) leaves the others
+ * waiting in their next exchange: treat it as fatal for the communicator.  The call works in an arena of its
+ * own that the peers map through CUDA IPC; it grows only after every rank has closed its mappings.        */
 #define BZAP_COMM_ID_BYTES 128
 int bzap_comm_unique_id(uint8_t id[BZAP_COMM_ID_BYTES]);
 int bzap_ctx_comm_init(bzap_ctx *ctx, const uint8_t id[BZAP_COMM_ID_BYTES], int world, int rank);
