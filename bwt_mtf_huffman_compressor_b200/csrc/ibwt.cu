@@ -155,17 +155,22 @@ ibwt_walk_len_kernel(const u32 *__restrict__ T, u32 n, u32 nb, u32 slog, u32 pri
     }
 }
 
-// one pointer-jumping round: dist[j] += dist[next[j]]; next[j] = next[next[j]]
+// one pointer-jumping round: dist[j] += dist[next[j]]; next[j] = next[next[j]] -- followed IB_HOPS times inside
+// the same snapshot `in`, so a round multiplies every node's span by IB_HOPS + 1 (three dependent loads instead
+// of one, but 11 launches instead of 21 for a million nodes: the rounds are launch bound at ~9 us each)
 // (nodes = the splitters, `primary`, and however many continuation nodes the walk appended: counter[1])
+#define IB_HOPS 3
 __global__ void __launch_bounds__(256)
 ibwt_wyllie_kernel(const u64 *__restrict__ in, u64 *__restrict__ out, u32 base_nodes, const u32 *__restrict__ counter)
 {
     const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= base_nodes + counter[1]) return;
     u64 a = in[j];
-    u32 nx = (u32)(a >> 32);
-    if (nx != IB_NIL) {
-        u64 b = in[nx];
+#pragma unroll
+    for (int h = 0; h < IB_HOPS; ++h) {
+        const u32 nx = (u32)(a >> 32);
+        if (nx == IB_NIL) break;
+        const u64 b = in[nx];
         a = (b & 0xffffffff00000000ull) | (u32)((u32)a + (u32)b);
     }
     out[j] = a;
@@ -221,10 +226,10 @@ int dev_ibwt(bzap_ctx *ctx, const u8 *d_last, size_t n64, u64 primary64, u8 *d_o
     LAUNCH(ctx, ibwt_walk_len_kernel, wgrid, 256, 0, d_T, n, nb, slog, primary, d_cum, d_len, d_slots, nodes, d_work);
     CU(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
     ctx->stats.walk_bytes = 5ull * n;            // T[row] (4 B) read + one slot byte written per row
-    // pointer jumping: after r rounds every node has jumped 2^r links
+    // pointer jumping: after r rounds every node has jumped (IB_HOPS + 1)^r links
     int cur = 0;
     const u64 *src = d_len;
-    for (u64 span = 1; span < nodes; span <<= 1) {
+    for (u64 span = 1; span < nodes; span *= (IB_HOPS + 1)) {
         LAUNCH(ctx, ibwt_wyllie_kernel, nblk, 256, 0, src, d_rank[cur], base_nodes, d_work);
         src = d_rank[cur];
         cur ^= 1;
