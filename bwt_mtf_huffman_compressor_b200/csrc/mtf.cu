@@ -13,9 +13,12 @@
 //
 // Inverse (replaces move_to_front_reverse, main.cpp:114-130).  Moves are position based, so the
 // net effect of a chunk is a permutation of list POSITIONS, independent of the list contents:
-//   1. imtf_perm_kernel   per chunk: run the moves on the identity list -> P_c (256 bytes);
-//   2. imtf_scan_*        scan of the permutations under composition, two levels;
-//   3. imtf_apply_kernel  per chunk: decode from its true start list.
+//   1. imtf_walk_kernel   per chunk: run the moves on the IDENTITY list -> P_c (256 bytes), and emit for every
+//                         input the position, in the chunk's (still unknown) start list, of the symbol it
+//                         selects -- the walk itself does not depend on what the list holds;
+//   2. imtf_scan_*        scan of the permutations under composition, two levels -> true start lists;
+//   3. imtf_map_kernel    out[i] = start_list[chunk(i)][position emitted in 1]: one table look-up per byte
+//                         (round 1 walked every chunk twice, once for P_c and once from its true list).
 //
 // A thread keeps its 256-entry list as 64 packed words in shared memory, laid out [word][thread]
 // (conflict free); a move-to-front is a byte-wise funnel shift over the first pos/4+1 words.
@@ -221,7 +224,7 @@ mtf_apply_kernel(const u8 *__restrict__ in, u32 n, u32 chunk, u32 nchunks, const
 
 // ---- inverse ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(MTF_THREADS)
-imtf_perm_kernel(const u8 *__restrict__ in, u32 n, u32 chunk, u32 nchunks, u8 *__restrict__ perms)
+imtf_walk_kernel(const u8 *__restrict__ in, u32 n, u32 chunk, u32 nchunks, u8 *__restrict__ perms, u8 *__restrict__ out)
 {
     __shared__ u32 s_list[64 * MTF_THREADS];
     const u32 c = blockIdx.x * MTF_THREADS + threadIdx.x;
@@ -235,10 +238,13 @@ imtf_perm_kernel(const u8 *__restrict__ in, u32 n, u32 chunk, u32 nchunks, u8 *_
     for (; p + 16 <= end; p += 16) {
         uint4 v = *reinterpret_cast<const uint4 *>(in + p);
         u32 ws[4] = {v.x, v.y, v.z, v.w};
+        u32 os[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int q = 0; q < 16; ++q) imtf_step(list, (ws[q >> 2] >> (8 * (q & 3))) & 0xffu);
+        for (int q = 0; q < 16; ++q)
+            os[q >> 2] |= imtf_step(list, (ws[q >> 2] >> (8 * (q & 3))) & 0xffu) << (8 * (q & 3));
+        *reinterpret_cast<uint4 *>(out + p) = make_uint4(os[0], os[1], os[2], os[3]);      // positions in the start list
     }
-    for (; p < end; ++p) imtf_step(list, in[p]);
+    for (; p < end; ++p) out[p] = (u8)imtf_step(list, in[p]);
     u32 *dst = reinterpret_cast<u32 *>(perms + (size_t)c * 256);
 #pragma unroll 8
     for (int k = 0; k < 64; ++k) dst[k] = list[k * MTF_THREADS];
@@ -294,30 +300,33 @@ imtf_lists_kernel(const u8 *__restrict__ perms, const u8 *__restrict__ group_tot
     lists[i] = group_tot[(size_t)g * 256 + perms[i]];
 }
 
-__global__ void __launch_bounds__(MTF_THREADS)
-imtf_apply_kernel(const u8 *__restrict__ in, u32 n, u32 chunk, u32 nchunks, const u8 *__restrict__ lists,
-                  u8 *__restrict__ out)
+// out[i] = lists[chunk(i)][out[i]], in place; one warp per chunk, its 256-byte start list in shared memory
+#define IMAP_WARPS 8
+__global__ void __launch_bounds__(32 * IMAP_WARPS)
+imtf_map_kernel(u8 *__restrict__ out, u32 n, u32 chunk, u32 nchunks, const u8 *__restrict__ lists)
 {
-    __shared__ u32 s_list[64 * MTF_THREADS];
-    const u32 c = blockIdx.x * MTF_THREADS + threadIdx.x;
+    __shared__ __align__(16) u8 s_list[IMAP_WARPS][256];
+    const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const u32 c = blockIdx.x * IMAP_WARPS + warp;
     if (c >= nchunks) return;
-    u32 *list = s_list + threadIdx.x;
-    const u32 *src = reinterpret_cast<const u32 *>(lists + (size_t)c * 256);
-#pragma unroll 8
-    for (int k = 0; k < 64; ++k) list[k * MTF_THREADS] = src[k];
+    reinterpret_cast<u64 *>(s_list[warp])[lane] = reinterpret_cast<const u64 *>(lists + (size_t)c * 256)[lane];
+    __syncwarp();
+    const u8 *L = s_list[warp];
     const u32 beg = c * chunk;
     const u32 end = min(n, beg + chunk);
-    u32 p = beg;
-    for (; p + 16 <= end; p += 16) {
-        uint4 v = *reinterpret_cast<const uint4 *>(in + p);
+    u32 p = beg + lane * 16;
+    for (; p + 16 <= end; p += 32 * 16) {
+        uint4 v = *reinterpret_cast<const uint4 *>(out + p);
         u32 ws[4] = {v.x, v.y, v.z, v.w};
-        u32 os[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int q = 0; q < 16; ++q)
-            os[q >> 2] |= imtf_step(list, (ws[q >> 2] >> (8 * (q & 3))) & 0xffu) << (8 * (q & 3));
-        *reinterpret_cast<uint4 *>(out + p) = make_uint4(os[0], os[1], os[2], os[3]);
+        for (int k = 0; k < 4; ++k)
+            ws[k] = (u32)L[ws[k] & 0xffu] | ((u32)L[(ws[k] >> 8) & 0xffu] << 8) | ((u32)L[(ws[k] >> 16) & 0xffu] << 16) |
+                    ((u32)L[ws[k] >> 24] << 24);
+        *reinterpret_cast<uint4 *>(out + p) = make_uint4(ws[0], ws[1], ws[2], ws[3]);
     }
-    for (; p < end; ++p) out[p] = (u8)imtf_step(list, in[p]);
+    // ragged tail of the last chunk (fewer than 16 bytes): the lane whose turn it would have been
+    if (p < end)
+        for (u32 q = p; q < end; ++q) out[q] = L[out[q]];
 }
 
 // ---- host drivers ------------------------------------------------------------------------------------
@@ -398,11 +407,11 @@ int dev_imtf(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_out)
     u8 *d_lists = arena_get<u8>(ctx, (size_t)nchunks * 256);
     if (!d_perms || !d_gtot || !d_lists) return bzap_fail(ctx, BZAP_ERR_NOMEM, "imtf scratch");
     const u32 cblocks = (nchunks + MTF_THREADS - 1) / MTF_THREADS;
-    LAUNCH(ctx, imtf_perm_kernel, cblocks, MTF_THREADS, 0, d_in, n, chunk, nchunks, d_perms);
+    LAUNCH(ctx, imtf_walk_kernel, cblocks, MTF_THREADS, 0, d_in, n, chunk, nchunks, d_perms, d_out);
     LAUNCH(ctx, imtf_scan_group_kernel, ngroups, 256, 0, d_perms, nchunks, d_gtot);
     LAUNCH(ctx, imtf_scan_top_kernel, 1, 256, 0, d_gtot, ngroups);
     LAUNCH(ctx, imtf_lists_kernel, (u32)(((size_t)nchunks * 256 + 255) / 256), 256, 0, d_perms, d_gtot, nchunks, d_lists);
-    LAUNCH(ctx, imtf_apply_kernel, cblocks, MTF_THREADS, 0, d_in, n, chunk, nchunks, d_lists, d_out);
+    LAUNCH(ctx, imtf_map_kernel, (nchunks + IMAP_WARPS - 1) / IMAP_WARPS, 32 * IMAP_WARPS, 0, d_out, n, chunk, nchunks, d_lists);
     CU(ctx, cudaGetLastError());
     return BZAP_OK;
 }
