@@ -312,6 +312,7 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline(data)
         sys.stdout.flush()
         os.write(result_fd, (json.dumps(line) + "\n").encode())
+    ctx.close()                      # collective when the ranks share a communicator: every rank gets here
     if dist is not None:
         dist.destroy_process_group()
 

@@ -142,8 +142,12 @@ void dist_comm_release(bzap_ctx *ctx)
     if (ctx->comm && g_nccl.ok) {
         if (ctx->dist_had_peers && ctx->dist_dev) {
             u32 *w = (u32 *)ctx->dist_dev;
-            if (g_nccl.AllReduce(w, w + 4, 1, ncclUint32, ncclSum, (ncclComm_t)ctx->comm, ctx->stream) == ncclSuccess)
-                cudaStreamSynchronize(ctx->stream);
+            if (g_nccl.AllReduce(w, w + 4, 1, ncclUint32, ncclSum, (ncclComm_t)ctx->comm, ctx->stream) == ncclSuccess) {
+                // bounded: a rank that died must not keep the survivors from shutting down
+                const auto t0 = std::chrono::steady_clock::now();
+                while (cudaStreamQuery(ctx->stream) == cudaErrorNotReady &&
+                       std::chrono::steady_clock::now() - t0 < std::chrono::seconds(5)) {}
+            }
         }
         g_nccl.CommDestroy((ncclComm_t)ctx->comm);
     }
