@@ -108,8 +108,9 @@ int dev_imtf(bzap_ctx *ctx, const u8 *d_in, size_t n, u8 *d_out);
 // the forward transform in two phases, for a piece of a block that starts from a handed-over list (dist_block.cu)
 struct MtfPlan {
     u32 n, chunk, nchunks, ngroups;
-    u32 *d_last, *d_gtot, *d_total;
+    u32 *d_last, *d_gtot, *d_total, *d_seg;
     u8 *d_lists;
+    int two_level;
 };
 size_t mtf_scratch_bytes(size_t n);
 int dev_mtf_begin(bzap_ctx *ctx, const u8 *d_in, size_t n, MtfPlan *plan);

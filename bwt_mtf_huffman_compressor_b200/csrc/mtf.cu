@@ -134,20 +134,27 @@ __global__ void __launch_bounds__(256) mtf_scan_group_kernel(u32 *__restrict__ l
     group_tot[(size_t)g * 256 + s] = run;
 }
 
-// total (may be null): the "last occurrence" summary of the whole input, i.e. what a following
-// piece of the same block needs to know about this one
-__global__ void __launch_bounds__(256) mtf_scan_top_kernel(u32 *__restrict__ group_tot, u32 ngroups, u32 *__restrict__ total)
+// Exclusive max-scan over the group totals.  Block b scans groups b * seg_len .. in place; with more than one
+// block the scan is two-level: seg_tot[b] receives the block's total, a second launch (one block) scans those,
+// and mtf_lists_kernel takes the maximum of both levels (592 groups: 19 + 19 dependent steps instead of 592).
+// total (may be null): the "last occurrence" summary of the whole input, i.e. what a following piece of the
+// same block needs to know about this one.
+#define MTF_SEG 32
+__global__ void __launch_bounds__(256)
+mtf_scan_top_kernel(u32 *__restrict__ group_tot, u32 ngroups, u32 seg_len, u32 *__restrict__ seg_tot, u32 *__restrict__ total)
 {
     const u32 s = threadIdx.x;
+    const u32 g0 = blockIdx.x * seg_len, g1 = min(ngroups, g0 + seg_len);
     u32 run = 0;
-    for (u32 g = 0; g < ngroups; g += 8) {
+    for (u32 g = g0; g < g1; g += 8) {
         u32 v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = g + i < ngroups ? group_tot[(size_t)(g + i) * 256 + s] : 0;
+        for (int i = 0; i < 8; ++i) v[i] = g + i < g1 ? group_tot[(size_t)(g + i) * 256 + s] : 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-            if (g + i < ngroups) { group_tot[(size_t)(g + i) * 256 + s] = run; run = max(run, v[i]); }
+            if (g + i < g1) { group_tot[(size_t)(g + i) * 256 + s] = run; run = max(run, v[i]); }
     }
+    if (seg_tot) seg_tot[(size_t)blockIdx.x * 256 + s] = run;
     if (total) total[s] = run;
 }
 
@@ -156,8 +163,8 @@ __global__ void __launch_bounds__(256) mtf_scan_top_kernel(u32 *__restrict__ gro
 // seen symbols (a few dozen on text) need ranking: they are compacted first, each is ranked against
 // the compacted keys, and an unseen symbol's slot follows from ballots alone.
 __global__ void __launch_bounds__(256)
-mtf_lists_kernel(const u32 *__restrict__ last, const u32 *__restrict__ group_tot, const u32 *__restrict__ init, u32 nchunks,
-                 u8 *__restrict__ lists)
+mtf_lists_kernel(const u32 *__restrict__ last, const u32 *__restrict__ group_tot, const u32 *__restrict__ seg_tot,
+                 const u32 *__restrict__ init, u32 nchunks, u8 *__restrict__ lists)
 {
     __shared__ __align__(16) u32 s_key[8][256];
     const u32 warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -170,6 +177,7 @@ mtf_lists_kernel(const u32 *__restrict__ last, const u32 *__restrict__ group_tot
     for (int i = 0; i < 8; ++i) {
         u32 s = lane + 32u * i;                       // symbols in increasing order over (i, lane)
         u32 k = max(last[(size_t)c * 256 + s], group_tot[(size_t)g * 256 + s]);
+        if (seg_tot) k = max(k, seg_tot[(size_t)(g / MTF_SEG) * 256 + s]);
         if (init) k = max(k, init[s]);
         key[i] = k;
         u32 m = __ballot_sync(FULL_MASK, k != 0);
@@ -272,13 +280,18 @@ __global__ void __launch_bounds__(256) imtf_scan_group_kernel(u8 *__restrict__ p
     group_tot[(size_t)g * 256 + j] = (u8)cur;
 }
 
-__global__ void __launch_bounds__(256) imtf_scan_top_kernel(u8 *__restrict__ group_tot, u32 ngroups)
+// Exclusive composition over the group totals, in place; two-level like the forward scan: block b composes
+// groups b * seg_len .., seg_tot[b] receives the block's composite, a second launch scans those, and
+// imtf_lists_kernel composes both levels (composition is associative: Top_g = Seg_b o Local_g).
+__global__ void __launch_bounds__(256)
+imtf_scan_top_kernel(u8 *__restrict__ group_tot, u32 ngroups, u32 seg_len, u8 *__restrict__ seg_tot)
 {
     __shared__ u8 s_cur[2][256];
     const u32 j = threadIdx.x;
+    const u32 g0 = blockIdx.x * seg_len, g1 = min(ngroups, g0 + seg_len);
     u32 cur = j;
     int buf = 0;
-    for (u32 g = 0; g < ngroups; ++g) {
+    for (u32 g = g0; g < g1; ++g) {
         u8 *row = group_tot + (size_t)g * 256;
         u32 pg = row[j];
         row[j] = (u8)cur;
@@ -287,17 +300,22 @@ __global__ void __launch_bounds__(256) imtf_scan_top_kernel(u8 *__restrict__ gro
         cur = s_cur[buf][pg];
         buf ^= 1;
     }
+    if (seg_tot) seg_tot[(size_t)blockIdx.x * 256 + j] = (u8)cur;
 }
 
-// start list of chunk c: A_c[j] = Top_g[ pre_c[j] ]   (the initial list is the identity, main.cpp:117-118)
+// start list of chunk c: A_c[j] = Top_g[ pre_c[j] ], Top_g = Seg_b o Local_g when the top scan ran in two levels
+// (the initial list is the identity, main.cpp:117-118)
 __global__ void __launch_bounds__(256)
-imtf_lists_kernel(const u8 *__restrict__ perms, const u8 *__restrict__ group_tot, u32 nchunks, u8 *__restrict__ lists)
+imtf_lists_kernel(const u8 *__restrict__ perms, const u8 *__restrict__ group_tot, const u8 *__restrict__ seg_tot, u32 nchunks,
+                  u8 *__restrict__ lists)
 {
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;   // byte index into the list array
     if (i >= (size_t)nchunks * 256) return;
     const u32 c = (u32)(i >> 8);
     const u32 g = c / MTF_GROUP;
-    lists[i] = group_tot[(size_t)g * 256 + perms[i]];
+    u32 v = group_tot[(size_t)g * 256 + perms[i]];
+    if (seg_tot) v = seg_tot[(size_t)(g / MTF_SEG) * 256 + v];
+    lists[i] = (u8)v;
 }
 
 // out[i] = lists[chunk(i)][out[i]], in place; one warp per chunk, its 256-byte start list in shared memory
@@ -345,7 +363,7 @@ size_t mtf_scratch_bytes(size_t n)
 {
     const u32 chunk = pick_chunk((u32)n);
     const size_t nchunks = (n + chunk - 1) / chunk + 2;
-    return nchunks * 1280 + (nchunks / MTF_GROUP + 2) * 1024 + 8192;
+    return nchunks * 1280 + (nchunks / MTF_GROUP + 2) * 1024 + (nchunks / MTF_GROUP / 32 + 4) * 1024 + 8192;
 }
 
 // phase 1: per-chunk "last occurrence" tables and their scans; plan->d_total[256] = summary of the whole input
@@ -361,7 +379,9 @@ int dev_mtf_begin(bzap_ctx *ctx, const u8 *d_in, size_t n64, MtfPlan *plan)
     plan->d_gtot = arena_get<u32>(ctx, (size_t)plan->ngroups * 256 + 256);
     plan->d_lists = arena_get<u8>(ctx, (size_t)plan->nchunks * 256 + 256);
     plan->d_total = arena_get<u32>(ctx, 256);
-    if (!plan->d_last || !plan->d_gtot || !plan->d_lists || !plan->d_total) return bzap_fail(ctx, BZAP_ERR_NOMEM, "mtf scratch");
+    plan->d_seg = arena_get<u32>(ctx, (size_t)(plan->ngroups / MTF_SEG + 2) * 256);
+    plan->two_level = 0;
+    if (!plan->d_last || !plan->d_gtot || !plan->d_lists || !plan->d_total || !plan->d_seg) return bzap_fail(ctx, BZAP_ERR_NOMEM, "mtf scratch");
     if (n == 0) {
         CU(ctx, cudaMemsetAsync(plan->d_total, 0, 256 * sizeof(u32), ctx->stream));
         return BZAP_OK;
@@ -370,7 +390,15 @@ int dev_mtf_begin(bzap_ctx *ctx, const u8 *d_in, size_t n64, MtfPlan *plan)
     CU(ctx, cudaMemsetAsync(plan->d_last, 0, (size_t)plan->nchunks * 256 * sizeof(u32), ctx->stream));
     LAUNCH(ctx, mtf_last_kernel, cblocks, MTF_THREADS, 0, d_in, n, plan->chunk, plan->nchunks, plan->d_last);
     LAUNCH(ctx, mtf_scan_group_kernel, plan->ngroups, 256, 0, plan->d_last, plan->nchunks, plan->d_gtot);
-    LAUNCH(ctx, mtf_scan_top_kernel, 1, 256, 0, plan->d_gtot, plan->ngroups, plan->d_total);
+    if (plan->ngroups > 2 * MTF_SEG) {
+        const u32 nseg = (plan->ngroups + MTF_SEG - 1) / MTF_SEG;
+        LAUNCH(ctx, mtf_scan_top_kernel, nseg, 256, 0, plan->d_gtot, plan->ngroups, (u32)MTF_SEG, plan->d_seg, (u32 *)nullptr);
+        LAUNCH(ctx, mtf_scan_top_kernel, 1, 256, 0, plan->d_seg, nseg, nseg, (u32 *)nullptr, plan->d_total);
+        plan->two_level = 1;
+    } else {
+        LAUNCH(ctx, mtf_scan_top_kernel, 1, 256, 0, plan->d_gtot, plan->ngroups, plan->ngroups, (u32 *)nullptr, plan->d_total);
+        plan->two_level = 0;
+    }
     CU(ctx, cudaGetLastError());
     return BZAP_OK;
 }
@@ -380,7 +408,8 @@ int dev_mtf_finish(bzap_ctx *ctx, const u8 *d_in, const MtfPlan *plan, const u32
 {
     if (plan->n == 0) return BZAP_OK;
     const u32 cblocks = (plan->nchunks + MTF_THREADS - 1) / MTF_THREADS;
-    LAUNCH(ctx, mtf_lists_kernel, (plan->nchunks + 7) / 8, 256, 0, plan->d_last, plan->d_gtot, d_init, plan->nchunks, plan->d_lists);
+    LAUNCH(ctx, mtf_lists_kernel, (plan->nchunks + 7) / 8, 256, 0, plan->d_last, plan->d_gtot,
+           plan->two_level ? (const u32 *)plan->d_seg : (const u32 *)nullptr, d_init, plan->nchunks, plan->d_lists);
     LAUNCH(ctx, mtf_apply_kernel, cblocks, MTF_THREADS, 0, d_in, plan->n, plan->chunk, plan->nchunks, plan->d_lists, d_out);
     CU(ctx, cudaGetLastError());
     return BZAP_OK;
@@ -405,12 +434,21 @@ int dev_imtf(bzap_ctx *ctx, const u8 *d_in, size_t n64, u8 *d_out)
     u8 *d_perms = arena_get<u8>(ctx, (size_t)nchunks * 256);
     u8 *d_gtot = arena_get<u8>(ctx, (size_t)ngroups * 256);
     u8 *d_lists = arena_get<u8>(ctx, (size_t)nchunks * 256);
-    if (!d_perms || !d_gtot || !d_lists) return bzap_fail(ctx, BZAP_ERR_NOMEM, "imtf scratch");
+    u8 *d_seg = arena_get<u8>(ctx, (size_t)(ngroups / MTF_SEG + 2) * 256);
+    if (!d_perms || !d_gtot || !d_lists || !d_seg) return bzap_fail(ctx, BZAP_ERR_NOMEM, "imtf scratch");
     const u32 cblocks = (nchunks + MTF_THREADS - 1) / MTF_THREADS;
     LAUNCH(ctx, imtf_walk_kernel, cblocks, MTF_THREADS, 0, d_in, n, chunk, nchunks, d_perms, d_out);
     LAUNCH(ctx, imtf_scan_group_kernel, ngroups, 256, 0, d_perms, nchunks, d_gtot);
-    LAUNCH(ctx, imtf_scan_top_kernel, 1, 256, 0, d_gtot, ngroups);
-    LAUNCH(ctx, imtf_lists_kernel, (u32)(((size_t)nchunks * 256 + 255) / 256), 256, 0, d_perms, d_gtot, nchunks, d_lists);
+    const bool two_level = ngroups > 2 * MTF_SEG;
+    if (two_level) {
+        const u32 nseg = (ngroups + MTF_SEG - 1) / MTF_SEG;
+        LAUNCH(ctx, imtf_scan_top_kernel, nseg, 256, 0, d_gtot, ngroups, (u32)MTF_SEG, d_seg);
+        LAUNCH(ctx, imtf_scan_top_kernel, 1, 256, 0, d_seg, nseg, nseg, (u8 *)nullptr);
+    } else {
+        LAUNCH(ctx, imtf_scan_top_kernel, 1, 256, 0, d_gtot, ngroups, ngroups, (u8 *)nullptr);
+    }
+    LAUNCH(ctx, imtf_lists_kernel, (u32)(((size_t)nchunks * 256 + 255) / 256), 256, 0, d_perms, d_gtot,
+           two_level ? (const u8 *)d_seg : (const u8 *)nullptr, nchunks, d_lists);
     LAUNCH(ctx, imtf_map_kernel, (nchunks + IMAP_WARPS - 1) / IMAP_WARPS, 32 * IMAP_WARPS, 0, d_out, n, chunk, nchunks, d_lists);
     CU(ctx, cudaGetLastError());
     return BZAP_OK;
