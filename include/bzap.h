@@ -146,7 +146,7 @@ int bzap_imtf(bzap_ctx *ctx, const uint8_t *in, size_t n, uint8_t *out);
 int bzap_hist256(bzap_ctx *ctx, const uint8_t *in, size_t n, uint64_t freq[256], uint8_t order[256], int *n_leaves);
 /* merge loop, main.cpp:245-254, with the pointer-order tie-break of the one-shot reference
  * binary.  Host only.  With BZAP_HEAP_REPLAY=1 in the environment, inputs below
- * 64,600 bytes take the order from bzap_heap_replay (an allocator replay, csrc/heap_replay.c)
+ * 64,600 bytes take the order from the allocator-replay helper (csrc/heap_replay.c)          
  * instead of the closed-form law: byte identity in the windows where the law does not hold.   */
 int bzap_huff_build(const uint64_t freq[256], const uint8_t *order, int n_leaves, bzap_tree *tree);
 /* traverse()/build_hashmap() main.cpp:132-156; code right-aligned in 64 bits, MSB-first       */
